@@ -1,0 +1,340 @@
+// HBM-bound kernels of the wav2vec2/WavLM/HuBERT path: waveform statistics, conv0 (+LayerNorm+GELU),
+// row LayerNorm (+GELU), layout scatter for the positional conv, hidden-state accumulation, masked mean pooling.
+#pragma once
+#include "common.cuh"
+
+namespace serenc {
+
+// ---------------------------------------------------------------------------------------------
+// Per-utterance waveform statistics: mean and 1/sqrt(var + 1e-7) over the valid samples
+// (Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm, HF feature_extraction_wav2vec2.py:77-97;
+//  population variance, two-pass like numpy's). One block per utterance.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) wav_stats_kernel(const float* __restrict__ wav,
+                                                          const UttSpan* __restrict__ utts,
+                                                          float2* __restrict__ stats /*[B] (mean, rstd)*/) {
+  const int b = blockIdx.x;
+  const float* x = wav + utts[b].sample_start;
+  const int n = utts[b].sample_len;
+  __shared__ double red[32];
+  __shared__ float s_mean;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_mean = (float)(v / (double)max(n, 1));
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = x[i] - mean;
+    acc += (double)(d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      const float var = (float)(v / (double)max(n, 1));
+      stats[b] = make_float2(mean, rsqrtf(var + 1e-7f));
+    }
+  }
+}
+
+// Apply the normalisation (used by the FeatureExtractor surface; the fused encode path normalises inside conv0).
+// Padding samples (i >= len) are written as 0, as HF does (feature_extraction_wav2vec2.py:90-93).
+__global__ void wav_normalize_kernel(const float* __restrict__ wav, const UttSpan* __restrict__ utts,
+                                     const float2* __restrict__ stats, float* __restrict__ out, int64_t out_stride,
+                                     int out_len) {
+  const int b = blockIdx.y;
+  const float2 st = stats[b];
+  const float* x = wav + utts[b].sample_start;
+  const int n = utts[b].sample_len;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < out_len; i += gridDim.x * blockDim.x)
+    out[b * out_stride + i] = i < n ? (x[i] - st.x) * st.y : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv0: Conv1d(1 -> 512, k=10, s=5) + LayerNorm(512) + exact GELU, channels-last bf16 output
+// (WavLMLayerNormConvLayer layer 0, HF modeling_wavlm.py:703-727). C_in = 1, so this is a bandwidth
+// kernel: 16 MFLOP but 3.3 MB of output per audio-second.
+//
+// Output "slot" layout: utterance b owns rows [row0[b], row0[b] + slot[b]) with row0 = 64*R6[b]; rows
+// t >= T0[b] inside the slot are written as zeros so every later layer sees finite, deterministic values.
+// Lane l of a warp owns channels {64*i + 2*l, 64*i + 2*l + 1 : i < 8} -> coalesced bf16x2 stores.
+// ---------------------------------------------------------------------------------------------
+constexpr int CONV0_C = 512;
+constexpr int CONV0_K = 10;
+constexpr int CONV0_S = 5;
+constexpr int CONV0_TILE = 256;  // frames per block
+
+typedef UttSpan Conv0Utt;
+
+__device__ __forceinline__ void conv0_finish(float (&a)[16], int t, bool in_tile, const Conv0Utt& u,
+                                             bf16* __restrict__ out, const float2* s_g, const float2* s_be,
+                                             int lane) {
+  if (!in_tile) return;  // warp-uniform
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + (u.row0 + t) * CONV0_C);
+  if (t >= u.T0) {  // slot padding rows: zeros
+#pragma unroll
+    for (int i = 0; i < 8; ++i) orow[32 * i + lane] = 0u;
+    return;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  const float mu = warp_sum(s) * (1.f / CONV0_C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float d = a[i] - mu;
+    q += d * d;
+  }
+  const float rs = rsqrtf(warp_sum(q) * (1.f / CONV0_C) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
+    const float y0 = gelu_erf((a[2 * i] - mu) * rs * g.x + be.x);
+    const float y1 = gelu_erf((a[2 * i + 1] - mu) * rs * g.y + be.y);
+    orow[32 * i + lane] = pack_bf16x2(y0, y1);
+  }
+}
+
+__global__ void __launch_bounds__(256) conv0_ln_gelu_kernel(const float* __restrict__ wav,
+                                                             const Conv0Utt* __restrict__ utts,
+                                                             const float2* __restrict__ stats,  // nullptr: already normalised
+                                                             const float* __restrict__ w,       // [512][10]
+                                                             const float* __restrict__ bias,    // [512] or nullptr
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             bf16* __restrict__ out) {
+  __shared__ float2 ws[CONV0_K][CONV0_C / 2];
+  __shared__ float2 s_b[CONV0_C / 2], s_g[CONV0_C / 2], s_be[CONV0_C / 2];
+  __shared__ float xs[CONV0_TILE * CONV0_S + CONV0_K];
+
+  const Conv0Utt u = utts[blockIdx.y];
+  const int t0 = blockIdx.x * CONV0_TILE;
+  if (t0 >= u.slot) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < CONV0_K * CONV0_C; i += blockDim.x) {
+    const int c = i / CONV0_K, j = i - c * CONV0_K;
+    reinterpret_cast<float*>(&ws[j][0])[c] = w[i];
+  }
+  for (int c = threadIdx.x; c < CONV0_C; c += blockDim.x) {
+    reinterpret_cast<float*>(s_b)[c] = bias ? bias[c] : 0.f;
+    reinterpret_cast<float*>(s_g)[c] = gamma[c];
+    reinterpret_cast<float*>(s_be)[c] = beta[c];
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (stats) {
+    const float2 st = stats[blockIdx.y];
+    mean = st.x;
+    rstd = st.y;
+  }
+  const float* x = wav + u.sample_start;
+  for (int i = threadIdx.x; i < CONV0_TILE * CONV0_S + CONV0_K; i += blockDim.x) {
+    const int64_t s = (int64_t)t0 * CONV0_S + i;
+    xs[i] = s < u.sample_len ? (x[s] - mean) * rstd : 0.f;
+  }
+  __syncthreads();
+
+  const int t_end = min(CONV0_TILE, u.slot - t0);
+  for (int f = warp * 2; f < t_end; f += 16) {
+    float a0[16], a1[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 b = s_b[32 * i + lane];
+      a0[2 * i] = b.x; a0[2 * i + 1] = b.y;
+      a1[2 * i] = b.x; a1[2 * i + 1] = b.y;
+    }
+#pragma unroll
+    for (int j = 0; j < CONV0_K; ++j) {
+      const float x0 = xs[f * CONV0_S + j];
+      const float x1 = xs[(f + 1) * CONV0_S + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 wv = ws[j][32 * i + lane];
+        a0[2 * i] = fmaf(wv.x, x0, a0[2 * i]);
+        a0[2 * i + 1] = fmaf(wv.y, x0, a0[2 * i + 1]);
+        a1[2 * i] = fmaf(wv.x, x1, a1[2 * i]);
+        a1[2 * i + 1] = fmaf(wv.y, x1, a1[2 * i + 1]);
+      }
+    }
+    conv0_finish(a0, t0 + f, f < t_end, u, out, s_g, s_be, lane);
+    conv0_finish(a1, t0 + f + 1, f + 1 < t_end, u, out, s_g, s_be, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row LayerNorm over C = 128*NV channels, one warp per row, fp32 statistics (eps 1e-5), optional GELU,
+// optional input gather (in_rowmap) and output scatter (out_rowmap). Serves the conv-layer LN+GELU
+// (bf16 -> bf16 in place), the feature-projection LN (bf16 gather -> bf16), the two LNs of every
+// transformer layer (fp32 residual stream -> bf16 GEMM operand) and the final LN (fp32 -> fp32).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <int NV, typename TIn, typename TOut, bool GELU>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
+                                                              TOut* __restrict__ out, int64_t ld_out,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int64_t rows,
+                                                              const int32_t* __restrict__ in_rowmap,
+                                                              const int32_t* __restrict__ out_rowmap, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t irow = in_rowmap ? (int64_t)in_rowmap[row] : row;
+  const int64_t orow = out_rowmap ? (int64_t)out_rowmap[row] : row;
+  if (irow < 0 || orow < 0) return;
+  const TIn* x = in + irow * ld_in;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = load4<TIn>(x + (lane + 32 * i) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  constexpr float invC = 1.f / (128.f * NV);
+  const float mu = warp_sum(s) * invC;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rs = rsqrtf(warp_sum(q) * invC + eps);
+  TOut* y = out + orow * ld_out;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+    o.x = (v[i].x - mu) * rs * g.x + be.x;
+    o.y = (v[i].y - mu) * rs * g.y + be.y;
+    o.z = (v[i].z - mu) * rs * g.z + be.z;
+    o.w = (v[i].w - mu) * rs * g.w + be.w;
+    if (GELU) {
+      o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+    }
+    store4<TOut>(y + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 packed residual stream -> bf16 rows of the positional-conv input buffer (zero gaps between
+// utterances = the conv's own zero padding; channels regrouped to g*cg_pad + c). Buffer is pre-zeroed.
+// ---------------------------------------------------------------------------------------------
+__global__ void scatter_posconv_in_kernel(const float* __restrict__ x, int64_t rows, int d, int cg, int cg_pad,
+                                          const int32_t* __restrict__ gap_row /*[rows]*/, bf16* __restrict__ out,
+                                          int64_t ld_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 channels
+  const int d4 = d >> 2;
+  if (idx >= rows * d4) return;
+  const int64_t r = idx / d4;
+  const int c = (int)(idx - r * d4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * d + c);
+  const int g = c / cg, cc = c - g * cg;  // cg % 4 == 0
+  store4<bf16>(out + (int64_t)gap_row[r] * ld_out + g * cg_pad + cc, v);
+}
+
+// acc = (first ? 0 : acc) + scale * x      (mean over selected hidden states, preprocess_speech.py:56-63)
+__global__ void accum_scaled_kernel(float* __restrict__ acc, const float* __restrict__ x, int64_t n4, float scale,
+                                    int first) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  float4 a = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(acc)[i];
+  a.x = fmaf(scale, v.x, a.x); a.y = fmaf(scale, v.y, a.y);
+  a.z = fmaf(scale, v.z, a.z); a.w = fmaf(scale, v.w, a.w);
+  reinterpret_cast<float4*>(acc)[i] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Masked mean pooling over the valid frames of each utterance (lora_wavlm/model.py:189-195 of the
+// reference): out[b, :] = sum_t x[off[b] + t, :] / n_b, t < n_b. Packed layout => the mask is the
+// frame range. Block = (128 columns, utterance b); 8 warps stride over frames, fixed-order smem
+// reduction => bitwise deterministic regardless of how utterances are sharded over GPUs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) masked_mean_pool_kernel(const float* __restrict__ x, int d,
+                                                                const int32_t* __restrict__ frame_off /*[B+1]*/,
+                                                                const int32_t* __restrict__ n_keep /*[B] or null*/,
+                                                                float* __restrict__ out /*[B, d]*/) {
+  __shared__ float4 red[8][32];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = frame_off[b];
+  int n = frame_off[b + 1] - r0;
+  if (n_keep) n = min(n, n_keep[b]);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < d) {
+    for (int t = warp; t < n; t += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)(r0 + t) * d + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < d) {
+    float4 a = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
+    }
+    const float inv = 1.f / (float)max(n, 1);
+    *reinterpret_cast<float4*>(out + (int64_t)b * d + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+
+// packed [sum T, d] -> padded [B, Tmax, d] (HF-shaped hidden states; pad frames are zero)
+__global__ void unpack_frames_kernel(const float* __restrict__ x, int d, const int32_t* __restrict__ frame_off,
+                                     int Tmax, float* __restrict__ out) {
+  const int b = blockIdx.z, t = blockIdx.y;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= d) return;
+  const int r0 = frame_off[b], n = frame_off[b + 1] - r0;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < n) v = *reinterpret_cast<const float4*>(x + (int64_t)(r0 + t) * d + c);
+  *reinterpret_cast<float4*>(out + ((int64_t)b * Tmax + t) * d + c) = v;
+}
+
+}  // namespace serenc

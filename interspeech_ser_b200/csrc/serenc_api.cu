@@ -1,0 +1,1307 @@
+// libserenc: C ABI + host-side runtime of the B200-native speech-SSL encoder forward.
+// See include/serenc.h for the contract each entry point replaces in the reference.
+#include "../../include/serenc.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <array>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "frontend_norm.cuh"
+#include "gemm_tcgen05.cuh"
+#include "logmel.cuh"
+
+using namespace serenc;
+
+// =================================================================================================
+// errors
+// =================================================================================================
+namespace {
+thread_local char g_err[1024] = "";
+}
+namespace serenc {
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace serenc
+
+#define SERENC_FAIL(code, ...)   \
+  do {                           \
+    serenc::set_error(__VA_ARGS__); \
+    return (code);               \
+  } while (0)
+
+// =================================================================================================
+// handle
+// =================================================================================================
+struct LayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  bf16* w_qkv;  // [3d, d]
+  float* b_qkv; // [3d]
+  bf16* w_o;    // [d, d]
+  float* b_o;
+  bf16* w_fc1;  // [ffn, d]
+  float* b_fc1;
+  bf16* w_fc2;  // [d, ffn]
+  float* b_fc2;
+  float *gru_w, *gru_b, *gru_const;  // WavLM: [8, hd], [8], [H]
+};
+
+static const int W2V_K[7] = {10, 3, 3, 3, 3, 2, 2};
+static const int W2V_S[7] = {5, 2, 2, 2, 2, 2, 2};
+
+struct serenc_handle {
+  serenc_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int head_dim = 64;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  std::set<std::string> loaded;
+  std::vector<LayerW> L;
+
+  // wav2vec2-family front end
+  float* conv0_w = nullptr;       // [512, 10]
+  bf16* conv_w[7] = {nullptr};    // 1..6: [512, k*512] tap-major
+  float* conv_b[7] = {nullptr};   // [512] (zeros when conv_bias = 0)
+  float* conv_g[7] = {nullptr};
+  float* conv_be[7] = {nullptr};
+  float *fp_g = nullptr, *fp_be = nullptr, *fp_b = nullptr;
+  bf16* fp_w = nullptr;           // [d, 512]
+  bf16* pos_w = nullptr;          // [d, taps * cg_pad]
+  float* pos_b = nullptr;
+  int pos_cg = 0, pos_cg_pad = 0;
+  float *fin_g = nullptr, *fin_b = nullptr;
+  std::vector<float> rel_embed_host;  // [num_buckets, H]
+  float* btab = nullptr;              // [H, 2*WAVLM_MAXD-1]
+
+  // whisper front end
+  bf16 *wc1 = nullptr, *wc2 = nullptr;  // [d, 3*n_mels_pad], [d, 3*d]
+  float *bc1 = nullptr, *bc2 = nullptr;
+  float* pos_emb = nullptr;             // [1500, d]
+  int mel_pad = 128;                    // n_mels rounded up to 64
+  std::vector<float> mel_filters_host;  // [201, n_mels]
+  float *hann = nullptr, *costab = nullptr, *sintab = nullptr, *mel_w = nullptr;
+  int32_t *mel_ptr = nullptr, *mel_bin = nullptr;
+
+  std::mutex mu;
+  std::map<std::array<uint64_t, 8>, CUtensorMap> tmaps;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(serenc_handle* h, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  SERENC_CUDA_OK(cudaMalloc(&p, bytes));
+  if (zero) SERENC_CUDA_OK(cudaMemset(p, 0, bytes));
+  h->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+int upload_f32(float* dst, const float* src, size_t n) {
+  SERENC_CUDA_OK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+int upload_bf16(bf16* dst, const std::vector<bf16>& src) {
+  SERENC_CUDA_OK(cudaMemcpy(dst, src.data(), src.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int64_t shape_numel(const int64_t* shape, int ndim) {
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// rank-2 bf16 map: dims {cols, rows}, row stride in bytes, box {64, box_rows}, 128B swizzle, zero OOB fill
+int get_tmap(serenc_handle* h, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+             uint32_t box_rows, CUtensorMap* out) {
+  std::array<uint64_t, 8> key = {reinterpret_cast<uint64_t>(base), cols, rows, row_stride_bytes, box_rows, 0, 0, 0};
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (rows == 0) rows = 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p cols=%llu rows=%llu stride=%llu box=%u",
+                (int)r, base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes,
+                box_rows);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  h->tmaps[key] = *out;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM launch
+// ---------------------------------------------------------------------------------------------
+struct GemmCall {
+  const bf16* A = nullptr;
+  int64_t a_cols = 0;         // channels per input row (tensor-map inner extent)
+  int64_t a_rows = 0;         // input rows available
+  int64_t a_ld = 0;           // elements between consecutive input rows
+  int a_stride = 1;           // temporal stride (1 | 2)
+  int a_kpt = 0;              // K-blocks per tap
+  int taps = 1;
+  int a_group_stride = 0;
+  int64_t M = 0;              // output rows
+  const bf16* W = nullptr;    // [w_rows, w_k], K index = tap * (a_kpt*64) + channel
+  int64_t w_rows = 0;
+  int64_t w_k = 0;            // elements per weight row (0: taps * a_kpt * 64)
+  int n_per_group = 0;
+  int groups = 1;
+  const float* bias = nullptr;
+  const float* resid = nullptr;
+  float* out_f32 = nullptr;
+  int64_t ld_f32 = 0;
+  bf16* out_bf16 = nullptr;
+  int64_t ld_bf16 = 0;
+  const int32_t* rowmap = nullptr;
+  int act = 0;
+};
+
+template <int BN>
+int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  GemmParams p;
+  p.M = c.M;
+  p.n_per_group = c.n_per_group;
+  p.groups = c.groups;
+  p.num_kb = c.taps * c.a_kpt;
+  p.tiles_m = (int)ceil_div64(c.M, GEMM_BM);
+  p.tiles_n = ceil_div(c.n_per_group, BN);
+  p.a_kpt = c.a_kpt;
+  p.a_stride = c.a_stride;
+  p.a_group_stride = c.a_group_stride;
+  p.bias = c.bias;
+  p.resid = c.resid;
+  p.out_f32 = c.out_f32;
+  p.ld_f32 = c.ld_f32;
+  p.out_bf16 = c.out_bf16;
+  p.ld_bf16 = c.ld_bf16;
+  p.rowmap = c.rowmap;
+  p.act = c.act;
+
+  CUtensorMap tA0, tA1, tB;
+  const uint64_t s = (uint64_t)c.a_stride;
+  // parity-p view of the input: rows p, p+s, p+2s, ...
+  SERENC_TRY(get_tmap(h, c.A, (uint64_t)c.a_cols, (uint64_t)ceil_div64(c.a_rows, (int64_t)s), (uint64_t)c.a_ld * s * 2,
+                      GEMM_BM, &tA0));
+  if (c.a_stride == 2) {
+    SERENC_TRY(get_tmap(h, c.A + c.a_ld, (uint64_t)c.a_cols, (uint64_t)(c.a_rows / 2 > 0 ? c.a_rows / 2 : 1),
+                        (uint64_t)c.a_ld * 4, GEMM_BM, &tA1));
+  } else {
+    tA1 = tA0;
+  }
+  const uint64_t wk = c.w_k > 0 ? (uint64_t)c.w_k : (uint64_t)p.num_kb * GEMM_BK;
+  SERENC_TRY(get_tmap(h, c.W, wk, (uint64_t)c.w_rows, wk * 2, BN, &tB));
+
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.groups;
+  if (tiles <= 0) return 0;
+  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
+  if (c.n_per_group % 8 != 0) SERENC_FAIL(SERENC_ERR_INVALID, "gemm: output width %d not a multiple of 8", c.n_per_group);
+  if ((c.a_ld % 8) != 0 || (c.a_group_stride % 8) != 0 || (c.w_k % 8) != 0)
+    SERENC_FAIL(SERENC_ERR_INVALID, "gemm: A leading dimension must be a multiple of 8 elements");
+  if (c.n_per_group <= 64) return launch_gemm_bn<64>(h, c, st);
+  if (c.n_per_group <= 128) return launch_gemm_bn<128>(h, c, st);
+  const int64_t tiles256 = ceil_div64(c.M, GEMM_BM) * ceil_div(c.n_per_group, 256) * c.groups;
+  if (tiles256 >= h->num_sms) return launch_gemm_bn<256>(h, c, st);
+  return launch_gemm_bn<128>(h, c, st);
+}
+
+// plain Linear: out = A[M, K] W[N, K]^T
+GemmCall linear_call(const bf16* A, int64_t M, int K, const bf16* W, int N) {
+  GemmCall c;
+  c.A = A;
+  c.a_cols = K;
+  c.a_rows = M;
+  c.a_ld = K;
+  c.a_stride = 1;
+  c.a_kpt = ceil_div(K, GEMM_BK);
+  c.taps = 1;
+  c.M = M;
+  c.W = W;
+  c.w_rows = N;
+  c.w_k = K;
+  c.n_per_group = N;
+  c.groups = 1;
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm launch
+// ---------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, bool GELU>
+int launch_ln_t(const TIn* in, int64_t ld_in, TOut* out, int64_t ld_out, const float* g, const float* b, int64_t rows,
+                int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  const int nv = cols / 128;
+  const dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+#define SERENC_LN_CASE(NV)                                                                                       \
+  case NV:                                                                                                       \
+    layernorm_rows_kernel<NV, TIn, TOut, GELU><<<grid, block, 0, st>>>(in, ld_in, out, ld_out, g, b, rows, in_map, \
+                                                                       out_map, eps);                            \
+    break;
+  switch (nv) {
+    SERENC_LN_CASE(1)
+    SERENC_LN_CASE(2)
+    SERENC_LN_CASE(3)
+    SERENC_LN_CASE(4)
+    SERENC_LN_CASE(5)
+    SERENC_LN_CASE(6)
+    SERENC_LN_CASE(8)
+    SERENC_LN_CASE(10)
+    SERENC_LN_CASE(12)
+    SERENC_LN_CASE(15)
+    SERENC_LN_CASE(16)
+    default:
+      SERENC_FAIL(SERENC_ERR_INVALID, "layernorm: unsupported width %d", cols);
+  }
+#undef SERENC_LN_CASE
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+bool ln_width_ok(int cols) {
+  if (cols % 128) return false;
+  const int nv = cols / 128;
+  return nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 5 || nv == 6 || nv == 8 || nv == 10 || nv == 12 || nv == 15 ||
+         nv == 16;
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention launch
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+int launch_attn_hd(const AttnParams& p, bool wavlm, int tmax, int heads, int batch, cudaStream_t st) {
+  const dim3 grid(ceil_div(tmax, ATT_BM), heads, batch), block(ATT_THREADS);
+  if (wavlm)
+    attention_fwd_kernel<HD, true><<<grid, block, AttnCfg<HD>::SMEM_BYTES, st>>>(p);
+  else
+    attention_fwd_kernel<HD, false><<<grid, block, AttnCfg<HD>::SMEM_BYTES, st>>>(p);
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, cudaStream_t st) {
+  if (batch <= 0 || tmax <= 0) return 0;
+  switch (h->head_dim) {
+    case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
+    case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
+    case 120: return launch_attn_hd<120>(p, wavlm, tmax, h->cfg.heads, batch, st);
+  }
+  SERENC_FAIL(SERENC_ERR_INVALID, "attention: unsupported head_dim %d", h->head_dim);
+}
+
+template <int HD>
+int set_attn_attr() {
+  SERENC_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      AttnCfg<HD>::SMEM_BYTES));
+  SERENC_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      AttnCfg<HD>::SMEM_BYTES));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving
+// ---------------------------------------------------------------------------------------------
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<uint8_t*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t used() const { return (off + 255) & ~size_t(255); }
+};
+
+// row maps built on the device from the per-utterance tables (keeps the per-call H2D copy tiny)
+__global__ void w2v_plan_kernel(const int32_t* __restrict__ frame_off, const int32_t* __restrict__ r6, int batch,
+                                int pad, int64_t sumT, int64_t mpos, int32_t* __restrict__ fp_gather,
+                                int32_t* __restrict__ gap_row, int32_t* __restrict__ pos_rowmap) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < sumT) {
+    int lo = 0, hi = batch - 1;  // largest b with frame_off[b] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (frame_off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    fp_gather[i] = r6[lo] + (int32_t)(i - frame_off[lo]);
+    gap_row[i] = (int32_t)i + pad * (lo + 1);
+  }
+  if (i < mpos) {
+    const int64_t q = i + pad;  // gapped row this GEMM row produces
+    int lo = 0, hi = batch - 1;  // largest b with gapped start <= q
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int64_t)frame_off[mid] + (int64_t)pad * (mid + 1) <= q) lo = mid; else hi = mid - 1;
+    }
+    const int64_t t = q - ((int64_t)frame_off[lo] + (int64_t)pad * (lo + 1));
+    const int64_t n = frame_off[lo + 1] - frame_off[lo];
+    pos_rowmap[i] = (t >= 0 && t < n) ? (int32_t)(frame_off[lo] + t) : -1;
+  }
+}
+
+__global__ void whisper_plan_kernel(int batch, int32_t* __restrict__ map1 /*[B*3002]*/, int32_t* __restrict__ map2 /*[B*1501]*/) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)batch * 3002) {
+    const int t = (int)(i % 3002);
+    map1[i] = t < 3000 ? (int32_t)(i + 1) : -1;
+  }
+  if (i < (int64_t)batch * 1501) {
+    const int b = (int)(i / 1501), t = (int)(i % 1501);
+    map2[i] = t < 1500 ? b * 1500 + t : -1;
+  }
+}
+
+int check_ready(serenc_handle* h, int arch) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  if (!h->finalized) SERENC_FAIL(SERENC_ERR_STATE, "handle not finalized (call serenc_finalize after loading tensors)");
+  if (arch >= 0 && h->cfg.arch != arch) SERENC_FAIL(SERENC_ERR_INVALID, "entry point does not match the handle's architecture");
+  SERENC_CUDA_OK(cudaSetDevice(h->device));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// pure host helpers (exported; testable without a GPU)
+// =================================================================================================
+extern "C" int64_t serenc_w2v_num_frames(int64_t n) {
+  for (int i = 0; i < 7; ++i) {
+    if (n < W2V_K[i]) return 0;
+    n = (n - W2V_K[i]) / W2V_S[i] + 1;
+  }
+  return n;
+}
+
+// WavLMAttention._relative_positions_bucket (HF modeling_wavlm.py:253-271), delta = key - query
+extern "C" int serenc_wavlm_bucket(int delta, int num_buckets, int max_distance) {
+  const int nb = num_buckets / 2;
+  int bucket = delta > 0 ? nb : 0;
+  const int a = delta < 0 ? -delta : delta;
+  const int max_exact = nb / 2;
+  if (a < max_exact) return bucket + a;
+  // HF evaluates this in fp32
+  float v = logf((float)a / (float)max_exact);
+  v = v / (float)log((double)max_distance / (double)max_exact);
+  v = v * (float)(nb - max_exact);
+  int large = max_exact + (int)v;
+  if (large > nb - 1) large = nb - 1;
+  return bucket + large;
+}
+
+extern "C" const char* serenc_last_error(void) { return g_err; }
+extern "C" const char* serenc_version(void) { return "serenc 0.1 (sm_100a; tcgen05 GEMM, mma.sync attention)"; }
+
+// =================================================================================================
+// lifecycle
+// =================================================================================================
+extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle** out) {
+  if (!cfg || !out) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    SERENC_FAIL(SERENC_ERR_NO_DEVICE, "no CUDA device visible: libserenc has no CPU fallback");
+  if (device < 0 || device >= ndev) SERENC_FAIL(SERENC_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+  cudaDeviceProp prop;
+  SERENC_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    SERENC_FAIL(SERENC_ERR_NO_DEVICE, "device %d is sm_%d%d; libserenc is built for sm_100a only", device, prop.major, prop.minor);
+  SERENC_CUDA_OK(cudaSetDevice(device));
+
+  const int d = cfg->hidden;
+  if (cfg->heads <= 0 || d % cfg->heads) SERENC_FAIL(SERENC_ERR_INVALID, "hidden %d not divisible by heads %d", d, cfg->heads);
+  const int hd = d / cfg->heads;
+  if (hd != 64 && hd != 80 && hd != 120) SERENC_FAIL(SERENC_ERR_INVALID, "head_dim %d unsupported (64, 80, 120)", hd);
+  if (!ln_width_ok(d)) SERENC_FAIL(SERENC_ERR_INVALID, "hidden size %d unsupported", d);
+  if (cfg->ffn % 64 || cfg->layers < 1 || cfg->layers > 63) SERENC_FAIL(SERENC_ERR_INVALID, "unsupported ffn/layers");
+
+  serenc_handle* h = new serenc_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->head_dim = hd;
+  *out = h;
+
+  int st = 0;
+  auto A = [&](auto** p, size_t n) { if (!st) st = dev_alloc(h, p, n); };
+  h->L.resize(cfg->layers);
+  for (auto& l : h->L) {
+    A(&l.ln1_g, d); A(&l.ln1_b, d); A(&l.ln2_g, d); A(&l.ln2_b, d);
+    A(&l.w_qkv, (size_t)3 * d * d); A(&l.b_qkv, 3 * d);
+    A(&l.w_o, (size_t)d * d); A(&l.b_o, d);
+    A(&l.w_fc1, (size_t)cfg->ffn * d); A(&l.b_fc1, cfg->ffn);
+    A(&l.w_fc2, (size_t)d * cfg->ffn); A(&l.b_fc2, d);
+    l.gru_w = l.gru_b = l.gru_const = nullptr;
+    if (cfg->wavlm_rel_bias) { A(&l.gru_w, 8 * hd); A(&l.gru_b, 8); A(&l.gru_const, cfg->heads); }
+  }
+  A(&h->fin_g, d); A(&h->fin_b, d);
+  if (cfg->arch == SERENC_ARCH_W2V) {
+    const int C = cfg->conv_dim;
+    if (C != CONV0_C) { st = SERENC_ERR_INVALID; serenc::set_error("conv_dim %d unsupported (512)", C); }
+    if (cfg->pos_conv_groups <= 0 || d % cfg->pos_conv_groups || (d / cfg->pos_conv_groups) % 8 || cfg->pos_conv_kernel < 1) {
+      st = SERENC_ERR_INVALID; serenc::set_error("unsupported positional conv configuration");
+    }
+    if (!st) {
+      A(&h->conv0_w, (size_t)C * W2V_K[0]);
+      for (int i = 0; i < 7; ++i) {
+        if (i > 0) A(&h->conv_w[i], (size_t)C * W2V_K[i] * C);
+        A(&h->conv_b[i], C); A(&h->conv_g[i], C); A(&h->conv_be[i], C);
+      }
+      A(&h->fp_g, C); A(&h->fp_be, C); A(&h->fp_w, (size_t)d * C); A(&h->fp_b, d);
+      h->pos_cg = d / cfg->pos_conv_groups;
+      h->pos_cg_pad = ceil_div(h->pos_cg, 64) * 64;
+      A(&h->pos_w, (size_t)d * cfg->pos_conv_kernel * h->pos_cg_pad); A(&h->pos_b, d);
+      if (cfg->wavlm_rel_bias) A(&h->btab, (size_t)cfg->heads * (2 * WAVLM_MAXD - 1));
+    }
+  } else if (cfg->arch == SERENC_ARCH_WHISPER) {
+    h->mel_pad = ceil_div(cfg->n_mels, 64) * 64;
+    A(&h->wc1, (size_t)d * 3 * h->mel_pad); A(&h->bc1, d);
+    A(&h->wc2, (size_t)d * 3 * d); A(&h->bc2, d);
+    A(&h->pos_emb, (size_t)cfg->max_source_positions * d);
+    if (cfg->max_source_positions != 1500 || d % 64) { st = SERENC_ERR_INVALID; serenc::set_error("whisper: max_source_positions must be 1500"); }
+  } else {
+    st = SERENC_ERR_INVALID;
+    serenc::set_error("unknown arch %d", cfg->arch);
+  }
+  if (!st) {
+    auto attr = [&](cudaError_t e) { if (e != cudaSuccess && !st) { st = SERENC_ERR_CUDA; serenc::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); } };
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES));
+    if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
+  }
+  if (st) {
+    serenc_destroy(h);
+    *out = nullptr;
+    return st;
+  }
+  return 0;
+}
+
+extern "C" int serenc_destroy(serenc_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+// conv weight [Cout, Cin, k] fp32 -> [Cout, k * cin_pad] bf16, K index = tap * cin_pad + c (zero padded)
+static std::vector<bf16> pack_conv(const float* w, int cout, int cin, int k, int cin_pad) {
+  std::vector<bf16> o((size_t)cout * k * cin_pad, __float2bfloat16(0.f));
+  for (int n = 0; n < cout; ++n)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < k; ++t)
+        o[((size_t)n * k + t) * cin_pad + c] = __float2bfloat16(w[((size_t)n * cin + c) * k + t]);
+  return o;
+}
+static std::vector<bf16> to_bf16(const float* w, size_t n) {
+  std::vector<bf16> o(n);
+  for (size_t i = 0; i < n; ++i) o[i] = __float2bfloat16(w[i]);
+  return o;
+}
+
+extern "C" int serenc_load_tensor(serenc_handle* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !name || !data || !shape) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  if (h->finalized) SERENC_FAIL(SERENC_ERR_STATE, "handle already finalized");
+  SERENC_CUDA_OK(cudaSetDevice(h->device));
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden, hd = h->head_dim;
+  const int64_t n = shape_numel(shape, ndim);
+  const std::string nm(name);
+  auto expect = [&](int64_t want) -> int {
+    if (n != want) SERENC_FAIL(SERENC_ERR_INVALID, "tensor %s: %lld elements, expected %lld", name, (long long)n, (long long)want);
+    return 0;
+  };
+  int li = -1, ci = -1;
+  char sub[64] = "";
+  int st = SERENC_ERR_INVALID;
+  bool known = true;
+
+  if (sscanf(name, "layer%d.%63s", &li, sub) == 2) {
+    if (li < 0 || li >= c.layers) SERENC_FAIL(SERENC_ERR_INVALID, "tensor %s: layer index out of range", name);
+    LayerW& l = h->L[li];
+    const std::string s(sub);
+    if (s == "ln1.weight") { SERENC_TRY(expect(d)); st = upload_f32(l.ln1_g, data, n); }
+    else if (s == "ln1.bias") { SERENC_TRY(expect(d)); st = upload_f32(l.ln1_b, data, n); }
+    else if (s == "ln2.weight") { SERENC_TRY(expect(d)); st = upload_f32(l.ln2_g, data, n); }
+    else if (s == "ln2.bias") { SERENC_TRY(expect(d)); st = upload_f32(l.ln2_b, data, n); }
+    else if (s == "q.weight" || s == "k.weight" || s == "v.weight") {
+      SERENC_TRY(expect((int64_t)d * d));
+      const int slot = s[0] == 'q' ? 0 : (s[0] == 'k' ? 1 : 2);
+      st = upload_bf16(l.w_qkv + (size_t)slot * d * d, to_bf16(data, n));
+    } else if (s == "q.bias" || s == "k.bias" || s == "v.bias") {
+      SERENC_TRY(expect(d));
+      const int slot = s[0] == 'q' ? 0 : (s[0] == 'k' ? 1 : 2);
+      st = upload_f32(l.b_qkv + (size_t)slot * d, data, n);
+    } else if (s == "o.weight") { SERENC_TRY(expect((int64_t)d * d)); st = upload_bf16(l.w_o, to_bf16(data, n)); }
+    else if (s == "o.bias") { SERENC_TRY(expect(d)); st = upload_f32(l.b_o, data, n); }
+    else if (s == "fc1.weight") { SERENC_TRY(expect((int64_t)c.ffn * d)); st = upload_bf16(l.w_fc1, to_bf16(data, n)); }
+    else if (s == "fc1.bias") { SERENC_TRY(expect(c.ffn)); st = upload_f32(l.b_fc1, data, n); }
+    else if (s == "fc2.weight") { SERENC_TRY(expect((int64_t)c.ffn * d)); st = upload_bf16(l.w_fc2, to_bf16(data, n)); }
+    else if (s == "fc2.bias") { SERENC_TRY(expect(d)); st = upload_f32(l.b_fc2, data, n); }
+    else if (c.wavlm_rel_bias && s == "gru.weight") { SERENC_TRY(expect(8 * hd)); st = upload_f32(l.gru_w, data, n); }
+    else if (c.wavlm_rel_bias && s == "gru.bias") { SERENC_TRY(expect(8)); st = upload_f32(l.gru_b, data, n); }
+    else if (c.wavlm_rel_bias && s == "gru.const") { SERENC_TRY(expect(c.heads)); st = upload_f32(l.gru_const, data, n); }
+    else known = false;
+  } else if (nm == "final_ln.weight") { SERENC_TRY(expect(d)); st = upload_f32(h->fin_g, data, n); }
+  else if (nm == "final_ln.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->fin_b, data, n); }
+  else if (c.arch == SERENC_ARCH_W2V && sscanf(name, "conv%d.%63s", &ci, sub) == 2) {
+    if (ci < 0 || ci > 6) SERENC_FAIL(SERENC_ERR_INVALID, "tensor %s: conv index out of range", name);
+    const std::string s(sub);
+    const int C = c.conv_dim;
+    if (s == "weight") {
+      if (ci == 0) { SERENC_TRY(expect((int64_t)C * W2V_K[0])); st = upload_f32(h->conv0_w, data, n); }
+      else { SERENC_TRY(expect((int64_t)C * C * W2V_K[ci])); st = upload_bf16(h->conv_w[ci], pack_conv(data, C, C, W2V_K[ci], C)); }
+    } else if (s == "bias") { SERENC_TRY(expect(C)); st = upload_f32(h->conv_b[ci], data, n); }
+    else if (s == "ln.weight") { SERENC_TRY(expect(C)); st = upload_f32(h->conv_g[ci], data, n); }
+    else if (s == "ln.bias") { SERENC_TRY(expect(C)); st = upload_f32(h->conv_be[ci], data, n); }
+    else known = false;
+  } else if (c.arch == SERENC_ARCH_W2V && nm == "featproj.ln.weight") { SERENC_TRY(expect(c.conv_dim)); st = upload_f32(h->fp_g, data, n); }
+  else if (c.arch == SERENC_ARCH_W2V && nm == "featproj.ln.bias") { SERENC_TRY(expect(c.conv_dim)); st = upload_f32(h->fp_be, data, n); }
+  else if (c.arch == SERENC_ARCH_W2V && nm == "featproj.weight") { SERENC_TRY(expect((int64_t)d * c.conv_dim)); st = upload_bf16(h->fp_w, to_bf16(data, n)); }
+  else if (c.arch == SERENC_ARCH_W2V && nm == "featproj.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->fp_b, data, n); }
+  else if (c.arch == SERENC_ARCH_W2V && nm == "posconv.weight") {
+    SERENC_TRY(expect((int64_t)d * h->pos_cg * c.pos_conv_kernel));
+    st = upload_bf16(h->pos_w, pack_conv(data, d, h->pos_cg, c.pos_conv_kernel, h->pos_cg_pad));
+  } else if (c.arch == SERENC_ARCH_W2V && nm == "posconv.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->pos_b, data, n); }
+  else if (c.arch == SERENC_ARCH_W2V && c.wavlm_rel_bias && nm == "rel_attn_embed") {
+    SERENC_TRY(expect((int64_t)c.num_buckets * c.heads));
+    h->rel_embed_host.assign(data, data + n);
+    st = 0;
+  } else if (c.arch == SERENC_ARCH_WHISPER && nm == "conv1.weight") {
+    SERENC_TRY(expect((int64_t)d * c.n_mels * 3));
+    st = upload_bf16(h->wc1, pack_conv(data, d, c.n_mels, 3, h->mel_pad));
+  } else if (c.arch == SERENC_ARCH_WHISPER && nm == "conv1.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->bc1, data, n); }
+  else if (c.arch == SERENC_ARCH_WHISPER && nm == "conv2.weight") {
+    SERENC_TRY(expect((int64_t)d * d * 3));
+    st = upload_bf16(h->wc2, pack_conv(data, d, d, 3, d));
+  } else if (c.arch == SERENC_ARCH_WHISPER && nm == "conv2.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->bc2, data, n); }
+  else if (c.arch == SERENC_ARCH_WHISPER && nm == "embed_positions") { SERENC_TRY(expect((int64_t)c.max_source_positions * d)); st = upload_f32(h->pos_emb, data, n); }
+  else if (c.arch == SERENC_ARCH_WHISPER && nm == "mel_filters") {
+    SERENC_TRY(expect((int64_t)LM_BINS * c.n_mels));
+    h->mel_filters_host.assign(data, data + n);
+    st = 0;
+  } else known = false;
+
+  if (!known) SERENC_FAIL(SERENC_ERR_INVALID, "unknown tensor name '%s' for this architecture", name);
+  if (st == 0) h->loaded.insert(nm);
+  return st;
+}
+
+extern "C" int serenc_finalize(serenc_handle* h) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  if (h->finalized) return 0;
+  SERENC_CUDA_OK(cudaSetDevice(h->device));
+  const serenc_config& c = h->cfg;
+  std::vector<std::string> req;
+  char buf[96];
+  for (int i = 0; i < c.layers; ++i) {
+    static const char* per[] = {"ln1.weight", "ln1.bias", "ln2.weight", "ln2.bias", "q.weight", "q.bias", "k.weight",
+                                "v.weight", "v.bias", "o.weight", "o.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"};
+    for (const char* s : per) { snprintf(buf, sizeof(buf), "layer%d.%s", i, s); req.push_back(buf); }
+    if (c.arch == SERENC_ARCH_W2V) { snprintf(buf, sizeof(buf), "layer%d.k.bias", i); req.push_back(buf); }  // Whisper's k_proj has no bias
+    if (c.wavlm_rel_bias) {
+      for (const char* s : {"gru.weight", "gru.bias", "gru.const"}) { snprintf(buf, sizeof(buf), "layer%d.%s", i, s); req.push_back(buf); }
+    }
+  }
+  req.push_back("final_ln.weight"); req.push_back("final_ln.bias");
+  if (c.arch == SERENC_ARCH_W2V) {
+    for (int i = 0; i < 7; ++i) {
+      snprintf(buf, sizeof(buf), "conv%d.weight", i); req.push_back(buf);
+      snprintf(buf, sizeof(buf), "conv%d.ln.weight", i); req.push_back(buf);
+      snprintf(buf, sizeof(buf), "conv%d.ln.bias", i); req.push_back(buf);
+      if (c.conv_bias) { snprintf(buf, sizeof(buf), "conv%d.bias", i); req.push_back(buf); }
+    }
+    for (const char* s : {"featproj.ln.weight", "featproj.ln.bias", "featproj.weight", "featproj.bias", "posconv.weight", "posconv.bias"}) req.push_back(s);
+    if (c.wavlm_rel_bias) req.push_back("rel_attn_embed");
+  } else {
+    for (const char* s : {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "embed_positions", "mel_filters"}) req.push_back(s);
+  }
+  for (const auto& r : req)
+    if (!h->loaded.count(r)) SERENC_FAIL(SERENC_ERR_STATE, "finalize: tensor '%s' was never loaded", r.c_str());
+
+  if (c.arch == SERENC_ARCH_W2V && c.wavlm_rel_bias) {
+    // bias_h[delta] = rel_attn_embed[bucket(delta), h]  (HF compute_bias, modeling_wavlm.py:243-251)
+    const int W = 2 * WAVLM_MAXD - 1;
+    std::vector<float> tab((size_t)c.heads * W);
+    for (int dlt = -(WAVLM_MAXD - 1); dlt <= WAVLM_MAXD - 1; ++dlt) {
+      const int bk = serenc_wavlm_bucket(dlt, c.num_buckets, c.max_distance);
+      for (int hh = 0; hh < c.heads; ++hh) tab[(size_t)hh * W + dlt + WAVLM_MAXD - 1] = h->rel_embed_host[(size_t)bk * c.heads + hh];
+    }
+    SERENC_TRY(upload_f32(h->btab, tab.data(), tab.size()));
+  }
+  if (c.arch == SERENC_ARCH_WHISPER) {
+    std::vector<float> hann(LM_NFFT), ct(LM_NFFT), stb(LM_NFFT);
+    const double PI = 3.14159265358979323846;
+    for (int i = 0; i < LM_NFFT; ++i) {
+      hann[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / LM_NFFT));  // torch.hann_window(400), periodic
+      ct[i] = (float)cos(2.0 * PI * i / LM_NFFT);
+      stb[i] = (float)sin(2.0 * PI * i / LM_NFFT);
+    }
+    std::vector<int32_t> ptr(c.n_mels + 1, 0), bin;
+    std::vector<float> w;
+    for (int m = 0; m < c.n_mels; ++m) {
+      for (int k = 0; k < LM_BINS; ++k) {
+        const float v = h->mel_filters_host[(size_t)k * c.n_mels + m];
+        if (v != 0.f) { bin.push_back(k); w.push_back(v); }
+      }
+      ptr[m + 1] = (int32_t)bin.size();
+    }
+    SERENC_TRY(dev_alloc(h, &h->hann, LM_NFFT)); SERENC_TRY(dev_alloc(h, &h->costab, LM_NFFT)); SERENC_TRY(dev_alloc(h, &h->sintab, LM_NFFT));
+    SERENC_TRY(dev_alloc(h, &h->mel_ptr, ptr.size())); SERENC_TRY(dev_alloc(h, &h->mel_bin, bin.size())); SERENC_TRY(dev_alloc(h, &h->mel_w, w.size()));
+    SERENC_TRY(upload_f32(h->hann, hann.data(), LM_NFFT)); SERENC_TRY(upload_f32(h->costab, ct.data(), LM_NFFT)); SERENC_TRY(upload_f32(h->sintab, stb.data(), LM_NFFT));
+    SERENC_CUDA_OK(cudaMemcpy(h->mel_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
+    SERENC_CUDA_OK(cudaMemcpy(h->mel_bin, bin.data(), bin.size() * 4, cudaMemcpyHostToDevice));
+    SERENC_TRY(upload_f32(h->mel_w, w.data(), w.size()));
+  }
+  SERENC_CUDA_OK(cudaDeviceSynchronize());
+  h->finalized = true;
+  return 0;
+}
+
+// =================================================================================================
+// shared transformer stack
+// =================================================================================================
+namespace {
+
+struct EmitCtx {
+  uint64_t mask;
+  int reduce;
+  int n_sel;
+  int sel = 0;
+  bool first = true;
+  float* frames_out;
+  float* pooled_out;
+  float* acc;  // REDUCE_MEAN accumulator ([sumT, d]); == frames_out when that is given
+  int64_t sumT;
+  int d;
+  int batch;
+  const int32_t* frame_off_dev;
+  const int32_t* n_keep_dev;
+};
+
+int pool_launch(const float* x, int d, int batch, const int32_t* foff, const int32_t* n_keep, float* out, cudaStream_t st) {
+  const dim3 grid(ceil_div(d, 128), batch);
+  masked_mean_pool_kernel<<<grid, 256, 0, st>>>(x, d, foff, n_keep, out);
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int emit_hidden(EmitCtx& e, int idx, const float* src, cudaStream_t st) {
+  if (!((e.mask >> idx) & 1ull)) return 0;
+  const int64_t n = e.sumT * e.d;
+  if (e.reduce == SERENC_REDUCE_NONE) {
+    if (e.frames_out)
+      SERENC_CUDA_OK(cudaMemcpyAsync(e.frames_out + (int64_t)e.sel * n, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (e.pooled_out)
+      SERENC_TRY(pool_launch(src, e.d, e.batch, e.frame_off_dev, e.n_keep_dev, e.pooled_out + (int64_t)e.sel * e.batch * e.d, st));
+  } else {
+    const int64_t n4 = n / 4;
+    accum_scaled_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(e.acc, src, n4, 1.0f / (float)e.n_sel, e.first ? 1 : 0);
+    SERENC_CUDA_OK(cudaGetLastError());
+    e.first = false;
+  }
+  e.sel++;
+  return 0;
+}
+
+struct StackBufs {
+  float* x;     // [sumT, d] fp32 residual stream (in/out)
+  float* xf;    // [sumT, d] fp32 final-LN output
+  bf16* hln;    // [sumT, d]
+  bf16* qkv;    // [sumT, 3d]
+  bf16* att;    // [sumT, d]
+  bf16* ffn;    // [sumT, ffn]
+};
+
+// Pre-LN ("stable layer norm") encoder stack + final LayerNorm, emitting the selected hidden states.
+// WavLMEncoderLayerStableLayerNorm / Wav2Vec2EncoderLayerStableLayerNorm / WhisperEncoderLayer
+// (HF modeling_wavlm.py:339-373, :450-522; modeling_whisper.py:361-414).
+int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int tmax, const int32_t* frame_off_dev,
+              EmitCtx& e, cudaStream_t st) {
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  SERENC_TRY(emit_hidden(e, 0, b.x, st));
+  for (int li = 0; li < c.layers; ++li) {
+    const LayerW& l = h->L[li];
+    SERENC_TRY((launch_ln_t<float, bf16, false>(b.x, d, b.hln, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+    {
+      GemmCall g = linear_call(b.hln, sumT, d, l.w_qkv, 3 * d);
+      g.bias = l.b_qkv; g.out_bf16 = b.qkv; g.ld_bf16 = 3 * d;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    {
+      AttnParams p;
+      p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
+      p.scale = 1.0f / sqrtf((float)h->head_dim);
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
+      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, st));
+    }
+    {
+      GemmCall g = linear_call(b.att, sumT, d, l.w_o, d);
+      g.bias = l.b_o; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    SERENC_TRY((launch_ln_t<float, bf16, false>(b.x, d, b.hln, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+    {
+      GemmCall g = linear_call(b.hln, sumT, d, l.w_fc1, c.ffn);
+      g.bias = l.b_fc1; g.act = 1; g.out_bf16 = b.ffn; g.ld_bf16 = c.ffn;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    {
+      GemmCall g = linear_call(b.ffn, sumT, c.ffn, l.w_fc2, d);
+      g.bias = l.b_fc2; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    if (li + 1 < c.layers) SERENC_TRY(emit_hidden(e, li + 1, b.x, st));
+  }
+  SERENC_TRY((launch_ln_t<float, float, false>(b.x, d, b.xf, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+  SERENC_TRY(emit_hidden(e, c.layers, b.xf, st));
+  if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
+    SERENC_TRY(pool_launch(e.acc, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
+  return 0;
+}
+
+int popcount64(uint64_t v) { int n = 0; while (v) { n += (int)(v & 1); v >>= 1; } return n; }
+
+// ---- wav2vec2-family plan ----
+struct W2VPlan {
+  int batch = 0;
+  std::vector<int32_t> T[7];
+  std::vector<int32_t> r6;      // slot row offset at layer 6
+  std::vector<int32_t> foff;    // [B+1]
+  int64_t r6_total = 0;
+  int64_t sumT = 0;
+  int tmax = 0;
+  int64_t rows[7];              // rows of every conv output buffer
+  int pad = 0;                  // pos-conv padding
+  int64_t rgap = 0, mpos = 0;
+};
+
+int make_w2v_plan(const serenc_handle* h, const int32_t* len, int batch, W2VPlan* p) {
+  if (batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "batch must be positive");
+  p->batch = batch;
+  for (int k = 0; k < 7; ++k) p->T[k].resize(batch);
+  p->r6.resize(batch);
+  p->foff.resize(batch + 1);
+  int64_t r6 = 0, sum = 0;
+  int tmax = 0;
+  for (int b = 0; b < batch; ++b) {
+    int64_t n = len[b];
+    for (int k = 0; k < 7; ++k) {
+      n = n < W2V_K[k] ? 0 : (n - W2V_K[k]) / W2V_S[k] + 1;
+      p->T[k][b] = (int32_t)n;
+    }
+    if (n < 1) SERENC_FAIL(SERENC_ERR_INVALID, "utterance %d has %d samples: shorter than the 400-sample receptive field (0 frames)", b, (int)len[b]);
+    p->r6[b] = (int32_t)r6;
+    p->foff[b] = (int32_t)sum;
+    r6 += n + 2;
+    sum += n;
+    if (n > tmax) tmax = (int)n;
+  }
+  p->foff[batch] = (int32_t)sum;
+  p->r6_total = r6;
+  p->sumT = sum;
+  p->tmax = tmax;
+  for (int k = 0; k < 7; ++k) p->rows[k] = r6 << (6 - k);
+  if (p->rows[0] >= (int64_t)1 << 31) SERENC_FAIL(SERENC_ERR_INVALID, "batch too large (conv0 rows overflow int32)");
+  p->pad = h->cfg.pos_conv_kernel / 2;
+  p->rgap = sum + (int64_t)p->pad * (batch + 1);
+  p->mpos = p->rgap - p->pad;
+  return 0;
+}
+
+struct W2VWs {
+  Conv0Utt* utts; float2* stats; int32_t* foff; int32_t* r6; int32_t *fp_gather, *gap_row, *pos_rowmap;
+  bf16 *cbuf0, *cbuf1; bf16* featln; bf16* posin;
+  StackBufs sb; float* acc;
+  size_t bytes;
+};
+
+void carve_w2v(const serenc_handle* h, const W2VPlan& p, void* base, W2VWs* w) {
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden, C = c.conv_dim;
+  Carver cv(base);
+  w->utts = cv.take<Conv0Utt>(p.batch);
+  w->stats = cv.take<float2>(p.batch);
+  w->foff = cv.take<int32_t>(p.batch + 1);
+  w->r6 = cv.take<int32_t>(p.batch);
+  w->fp_gather = cv.take<int32_t>(p.sumT);
+  w->gap_row = cv.take<int32_t>(p.sumT);
+  w->pos_rowmap = cv.take<int32_t>(p.mpos);
+  w->cbuf0 = cv.take<bf16>((size_t)p.rows[0] * C);  // conv0, conv2, conv4, conv6 outputs
+  w->cbuf1 = cv.take<bf16>((size_t)p.rows[1] * C);  // conv1, conv3, conv5 outputs
+  w->featln = cv.take<bf16>((size_t)p.sumT * C);
+  w->posin = cv.take<bf16>((size_t)p.rgap * c.pos_conv_groups * h->pos_cg_pad);
+  w->sb.x = cv.take<float>((size_t)p.sumT * d);
+  w->sb.xf = cv.take<float>((size_t)p.sumT * d);
+  w->sb.hln = cv.take<bf16>((size_t)p.sumT * d);
+  w->sb.qkv = cv.take<bf16>((size_t)p.sumT * 3 * d);
+  w->sb.att = cv.take<bf16>((size_t)p.sumT * d);
+  w->sb.ffn = cv.take<bf16>((size_t)p.sumT * c.ffn);
+  w->acc = cv.take<float>((size_t)p.sumT * d);
+  w->bytes = cv.used();
+}
+
+// small per-call metadata goes through a thread-local pinned staging buffer
+struct Staging {
+  void* host = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+  bool pending = false;
+};
+thread_local Staging g_stage;
+
+int stage_reserve(size_t bytes, void** out) {
+  Staging& s = g_stage;
+  if (s.pending) { SERENC_CUDA_OK(cudaEventSynchronize(s.ev)); s.pending = false; }
+  if (bytes > s.cap) {
+    if (s.host) cudaFreeHost(s.host);
+    s.host = nullptr; s.cap = 0;
+    const size_t cap = (bytes + 65535) & ~size_t(65535);
+    SERENC_CUDA_OK(cudaMallocHost(&s.host, cap));
+    s.cap = cap;
+  }
+  if (!s.ev) SERENC_CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  *out = s.host;
+  return 0;
+}
+int stage_commit(cudaStream_t st) {
+  SERENC_CUDA_OK(cudaEventRecord(g_stage.ev, st));
+  g_stage.pending = true;
+  return 0;
+}
+
+// stage a [batch] UttSpan table (sample ranges only) and copy it to `dst_dev`
+int upload_spans(const int64_t* sample_start, const int32_t* sample_len, int batch, UttSpan* dst_dev, cudaStream_t st) {
+  void* hs;
+  SERENC_TRY(stage_reserve(sizeof(UttSpan) * (size_t)batch, &hs));
+  UttSpan* hu = reinterpret_cast<UttSpan*>(hs);
+  for (int b = 0; b < batch; ++b) {
+    hu[b].sample_start = sample_start[b];
+    hu[b].sample_len = sample_len[b];
+    hu[b].T0 = 0; hu[b].row0 = 0; hu[b].slot = 0; hu[b].pad_ = 0;
+  }
+  SERENC_CUDA_OK(cudaMemcpyAsync(dst_dev, hu, sizeof(UttSpan) * (size_t)batch, cudaMemcpyHostToDevice, st));
+  return stage_commit(st);
+}
+
+}  // namespace
+
+// =================================================================================================
+// wav2vec2 / HuBERT / WavLM
+// =================================================================================================
+extern "C" int serenc_w2v_workspace_bytes(const serenc_handle* h, const int32_t* sample_len, int batch, size_t* out_bytes) {
+  if (!h || !sample_len || !out_bytes) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  if (h->cfg.arch != SERENC_ARCH_W2V) SERENC_FAIL(SERENC_ERR_INVALID, "not a wav2vec2-family handle");
+  W2VPlan p;
+  SERENC_TRY(make_w2v_plan(h, sample_len, batch, &p));
+  W2VWs w;
+  carve_w2v(h, p, nullptr, &w);
+  *out_bytes = w.bytes + 256;
+  return 0;
+}
+
+extern "C" int serenc_wav_normalize(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                                    int batch, float* out_dev, int64_t out_stride, int32_t out_len, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  if (!wav_dev || !sample_start || !sample_len || !out_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // tiny device scratch (span table + stats) from the stream-ordered pool
+  void* dscratch;
+  SERENC_CUDA_OK(cudaMallocAsync(&dscratch, (size_t)batch * (sizeof(UttSpan) + sizeof(float2)) + 64, st));
+  UttSpan* d_utts = reinterpret_cast<UttSpan*>(dscratch);
+  float2* d_stats = reinterpret_cast<float2*>(d_utts + batch);
+  SERENC_TRY(upload_spans(sample_start, sample_len, batch, d_utts, st));
+  wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, d_utts, d_stats);
+  SERENC_CUDA_OK(cudaGetLastError());
+  const dim3 grid(ceil_div(out_len, 1024) < 64 ? ceil_div(out_len, 1024) : 64, batch);
+  wav_normalize_kernel<<<grid, 256, 0, st>>>(wav_dev, d_utts, d_stats, out_dev, out_stride, out_len);
+  SERENC_CUDA_OK(cudaGetLastError());
+  SERENC_CUDA_OK(cudaFreeAsync(dscratch, st));
+  return 0;
+}
+
+extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                                 int batch, int normalize, uint64_t layer_mask, int reduce, float* frames_out_dev,
+                                 float* pooled_out_dev, int64_t* frame_offsets_out, void* workspace_dev, size_t workspace_bytes,
+                                 void* stream) {
+  SERENC_TRY(check_ready(h, SERENC_ARCH_W2V));
+  if (!wav_dev || !sample_start || !sample_len || !workspace_dev) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden, C = c.conv_dim;
+  if (c.layers < 63) layer_mask &= ((1ull << (c.layers + 1)) - 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+  W2VPlan p;
+  SERENC_TRY(make_w2v_plan(h, sample_len, batch, &p));
+  W2VWs w;
+  carve_w2v(h, p, workspace_dev, &w);
+  if (w.bytes > workspace_bytes) SERENC_FAIL(SERENC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  if (frame_offsets_out) for (int b = 0; b <= batch; ++b) frame_offsets_out[b] = p.foff[b];
+
+  // ---- per-utterance tables -> device ----
+  {
+    const size_t sz_u = sizeof(Conv0Utt) * batch, sz_f = 4 * (size_t)(batch + 1), sz_r = 4 * (size_t)batch;
+    void* hs;
+    SERENC_TRY(stage_reserve(sz_u + sz_f + sz_r + 64, &hs));
+    Conv0Utt* hu = reinterpret_cast<Conv0Utt*>(hs);
+    for (int b = 0; b < batch; ++b) {
+      hu[b].sample_start = sample_start[b];
+      hu[b].sample_len = sample_len[b];
+      hu[b].T0 = p.T[0][b];
+      hu[b].row0 = (int64_t)p.r6[b] << 6;
+      hu[b].slot = (p.T[6][b] + 2) << 6;
+      hu[b].pad_ = 0;
+    }
+    int32_t* hf = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(hs) + sz_u);
+    memcpy(hf, p.foff.data(), sz_f);
+    int32_t* hr = hf + batch + 1;
+    memcpy(hr, p.r6.data(), sz_r);
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.utts, hu, sz_u, cudaMemcpyHostToDevice, st));
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.foff, hf, sz_f, cudaMemcpyHostToDevice, st));
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.r6, hr, sz_r, cudaMemcpyHostToDevice, st));
+    SERENC_TRY(stage_commit(st));
+    const int64_t nthreads = p.sumT > p.mpos ? p.sumT : p.mpos;
+    w2v_plan_kernel<<<(unsigned)ceil_div64(nthreads, 256), 256, 0, st>>>(w.foff, w.r6, batch, p.pad, p.sumT, p.mpos, w.fp_gather, w.gap_row, w.pos_rowmap);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
+
+  // ---- feature encoder: conv0 (+norm stats) then conv1..6 as implicit GEMMs, each followed by LN + GELU ----
+  {
+    if (normalize) {
+      wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, w.utts, w.stats);
+      SERENC_CUDA_OK(cudaGetLastError());
+    }
+    int slot_max = 0;
+    for (int b = 0; b < batch; ++b) slot_max = slot_max > ((p.T[6][b] + 2) << 6) ? slot_max : ((p.T[6][b] + 2) << 6);
+    const dim3 grid(ceil_div(slot_max, CONV0_TILE), batch);
+    conv0_ln_gelu_kernel<<<grid, 256, 0, st>>>(wav_dev, w.utts, normalize ? w.stats : nullptr, h->conv0_w,
+                                               c.conv_bias ? h->conv_b[0] : nullptr, h->conv_g[0], h->conv_be[0], w.cbuf0);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
+  bf16* cin = w.cbuf0;
+  bf16* cout = w.cbuf1;
+  for (int k = 1; k < 7; ++k) {
+    GemmCall g;
+    g.A = cin; g.a_cols = C; g.a_rows = p.rows[k - 1]; g.a_ld = C; g.a_stride = W2V_S[k]; g.a_kpt = C / GEMM_BK; g.taps = W2V_K[k];
+    g.M = p.rows[k]; g.W = h->conv_w[k]; g.w_rows = C; g.n_per_group = C; g.groups = 1;
+    g.bias = c.conv_bias ? h->conv_b[k] : nullptr;
+    g.out_bf16 = cout; g.ld_bf16 = C;
+    SERENC_TRY(launch_gemm(h, g, st));
+    SERENC_TRY((launch_ln_t<bf16, bf16, true>(cout, C, cout, C, h->conv_g[k], h->conv_be[k], p.rows[k], C, nullptr, nullptr, 1e-5f, st)));
+    bf16* t = cin; cin = cout; cout = t;
+  }
+  // ---- feature projection: LN(512) over the valid frames (gathered into the packed layout) -> Linear(512 -> d) ----
+  SERENC_TRY((launch_ln_t<bf16, bf16, false>(cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
+  {
+    GemmCall g = linear_call(w.featln, p.sumT, C, h->fp_w, d);
+    g.bias = h->fp_b; g.out_f32 = w.sb.x; g.ld_f32 = d;
+    SERENC_TRY(launch_gemm(h, g, st));
+  }
+  // ---- positional conv embedding: x += gelu(grouped_conv(x) + b) ----
+  {
+    const int64_t ld_pos = (int64_t)c.pos_conv_groups * h->pos_cg_pad;
+    SERENC_CUDA_OK(cudaMemsetAsync(w.posin, 0, (size_t)p.rgap * ld_pos * sizeof(bf16), st));
+    const int64_t nthr = p.sumT * (d / 4);
+    scatter_posconv_in_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(w.sb.x, p.sumT, d, h->pos_cg, h->pos_cg_pad, w.gap_row, w.posin, ld_pos);
+    SERENC_CUDA_OK(cudaGetLastError());
+    GemmCall g;
+    g.A = w.posin; g.a_cols = ld_pos; g.a_rows = p.rgap; g.a_ld = ld_pos; g.a_stride = 1; g.a_kpt = h->pos_cg_pad / GEMM_BK;
+    g.taps = c.pos_conv_kernel; g.a_group_stride = h->pos_cg_pad;
+    g.M = p.mpos; g.W = h->pos_w; g.w_rows = d; g.n_per_group = h->pos_cg; g.groups = c.pos_conv_groups;
+    g.bias = h->pos_b; g.act = 1; g.resid = w.sb.x; g.out_f32 = w.sb.x; g.ld_f32 = d; g.rowmap = w.pos_rowmap;
+    SERENC_TRY(launch_gemm(h, g, st));
+  }
+  // ---- transformer stack ----
+  EmitCtx e;
+  e.mask = layer_mask; e.reduce = reduce; e.n_sel = popcount64(layer_mask);
+  e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
+  e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
+  e.sumT = p.sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = nullptr;
+  SERENC_TRY(run_stack(h, w.sb, p.sumT, batch, p.tmax, w.foff, e, st));
+  return 0;
+}
+
+extern "C" int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
+                                    int32_t t_max, float* out_dev, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  if (!packed_dev || !frame_offsets || !out_dev || batch <= 0 || t_max <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int d = h->cfg.hidden;
+  int32_t* d_off;
+  SERENC_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_off), 4 * (size_t)(batch + 1), st));
+  void* hs;
+  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs));
+  for (int b = 0; b <= batch; ++b) reinterpret_cast<int32_t*>(hs)[b] = (int32_t)frame_offsets[b];
+  SERENC_CUDA_OK(cudaMemcpyAsync(d_off, hs, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
+  SERENC_TRY(stage_commit(st));
+  const dim3 grid(ceil_div(d / 4, 128), t_max, batch);
+  unpack_frames_kernel<<<grid, 128, 0, st>>>(packed_dev, d, d_off, t_max, out_dev);
+  SERENC_CUDA_OK(cudaGetLastError());
+  SERENC_CUDA_OK(cudaFreeAsync(d_off, st));
+  return 0;
+}
+
+// =================================================================================================
+// Whisper
+// =================================================================================================
+extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                             int batch, float* mel_out_dev, void* scratch_dev, void* stream) {
+  SERENC_TRY(check_ready(h, SERENC_ARCH_WHISPER));
+  if (!wav_dev || !sample_start || !sample_len || !mel_out_dev || !scratch_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // scratch layout: [batch] ordered-max words, then the span table
+  UttSpan* d_utts = reinterpret_cast<UttSpan*>(reinterpret_cast<uint8_t*>(scratch_dev) + (((size_t)batch * 4 + 63) & ~size_t(63)));
+  SERENC_TRY(upload_spans(sample_start, sample_len, batch, d_utts, st));
+  uint32_t* umax = reinterpret_cast<uint32_t*>(scratch_dev);
+  SERENC_CUDA_OK(cudaMemsetAsync(umax, 0, 4 * (size_t)batch, st));
+  LogmelTables tb;
+  tb.hann = h->hann; tb.costab = h->costab; tb.sintab = h->sintab;
+  tb.mel_ptr = h->mel_ptr; tb.mel_bin = h->mel_bin; tb.mel_w = h->mel_w; tb.n_mels = h->cfg.n_mels;
+  const dim3 grid(ceil_div(LM_FRAMES, LM_FR), batch);
+  logmel_power_kernel<<<grid, LM_THREADS, 0, st>>>(wav_dev, d_utts, tb, mel_out_dev, umax);
+  SERENC_CUDA_OK(cudaGetLastError());
+  const int64_t per_utt = (int64_t)h->cfg.n_mels * LM_FRAMES;
+  logmel_finalize_kernel<<<dim3(64, batch), 256, 0, st>>>(mel_out_dev, umax, per_utt);
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+namespace {
+struct WhisperWs {
+  int32_t *map1, *map2, *foff, *n_keep;
+  bf16 *melrows, *c1;
+  StackBufs sb; float* acc;
+  size_t bytes;
+};
+void carve_whisper(const serenc_handle* h, int batch, void* base, WhisperWs* w) {
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  const int64_t sumT = (int64_t)batch * 1500;
+  Carver cv(base);
+  w->map1 = cv.take<int32_t>((size_t)batch * 3002);
+  w->map2 = cv.take<int32_t>((size_t)batch * 1501);
+  w->foff = cv.take<int32_t>(batch + 1);
+  w->n_keep = cv.take<int32_t>(batch);
+  w->melrows = cv.take<bf16>((size_t)batch * 3002 * h->mel_pad);
+  w->c1 = cv.take<bf16>((size_t)batch * 3002 * d);
+  w->sb.x = cv.take<float>((size_t)sumT * d);
+  w->sb.xf = cv.take<float>((size_t)sumT * d);
+  w->sb.hln = cv.take<bf16>((size_t)sumT * d);
+  w->sb.qkv = cv.take<bf16>((size_t)sumT * 3 * d);
+  w->sb.att = cv.take<bf16>((size_t)sumT * d);
+  w->sb.ffn = cv.take<bf16>((size_t)sumT * c.ffn);
+  w->acc = cv.take<float>((size_t)sumT * d);
+  w->bytes = cv.used();
+}
+}  // namespace
+
+extern "C" int serenc_whisper_workspace_bytes(const serenc_handle* h, int batch, size_t* out_bytes) {
+  if (!h || !out_bytes || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  if (h->cfg.arch != SERENC_ARCH_WHISPER) SERENC_FAIL(SERENC_ERR_INVALID, "not a Whisper handle");
+  WhisperWs w;
+  carve_whisper(h, batch, nullptr, &w);
+  *out_bytes = w.bytes + 256;
+  return 0;
+}
+
+extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
+                                     const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+  SERENC_TRY(check_ready(h, SERENC_ARCH_WHISPER));
+  if (!mel_dev || !workspace_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  if (c.layers < 63) layer_mask &= ((1ull << (c.layers + 1)) - 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  WhisperWs w;
+  carve_whisper(h, batch, workspace_dev, &w);
+  if (w.bytes > workspace_bytes) SERENC_FAIL(SERENC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  const int64_t sumT = (int64_t)batch * 1500;
+
+  {
+    void* hs;
+    SERENC_TRY(stage_reserve(4 * (size_t)(2 * batch + 1), &hs));
+    int32_t* hf = reinterpret_cast<int32_t*>(hs);
+    for (int b = 0; b <= batch; ++b) hf[b] = b * 1500;
+    for (int b = 0; b < batch; ++b) hf[batch + 1 + b] = n_keep ? (n_keep[b] < 1 ? 1 : (n_keep[b] > 1500 ? 1500 : n_keep[b])) : 1500;
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.foff, hf, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.n_keep, hf + batch + 1, 4 * (size_t)batch, cudaMemcpyHostToDevice, st));
+    SERENC_TRY(stage_commit(st));
+    whisper_plan_kernel<<<(unsigned)ceil_div64((int64_t)batch * 3002, 256), 256, 0, st>>>(batch, w.map1, w.map2);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
+  // conv stem (HF modeling_whisper.py:619-625): gelu(conv1 k3 p1) -> gelu(conv2 k3 s2 p1) -> + positions
+  SERENC_CUDA_OK(cudaMemsetAsync(w.melrows, 0, (size_t)batch * 3002 * h->mel_pad * sizeof(bf16), st));
+  {
+    const dim3 grid(ceil_div(LM_FRAMES, 32), ceil_div(c.n_mels, 32), batch);
+    mel_to_rows_kernel<<<grid, 256, 0, st>>>(mel_dev, c.n_mels, w.melrows, h->mel_pad);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
+  SERENC_CUDA_OK(cudaMemsetAsync(w.c1, 0, (size_t)batch * 3002 * d * sizeof(bf16), st));
+  {
+    GemmCall g;
+    g.A = w.melrows; g.a_cols = h->mel_pad; g.a_rows = (int64_t)batch * 3002; g.a_ld = h->mel_pad; g.a_stride = 1;
+    g.a_kpt = h->mel_pad / GEMM_BK; g.taps = 3;
+    g.M = (int64_t)batch * 3002; g.W = h->wc1; g.w_rows = d; g.n_per_group = d; g.groups = 1;
+    g.bias = h->bc1; g.act = 1; g.out_bf16 = w.c1; g.ld_bf16 = d; g.rowmap = w.map1;
+    SERENC_TRY(launch_gemm(h, g, st));
+  }
+  {
+    const int64_t per_utt4 = (int64_t)1500 * d / 4;
+    broadcast_rows_kernel<<<dim3(128, batch), 256, 0, st>>>(h->pos_emb, per_utt4, w.sb.x);
+    SERENC_CUDA_OK(cudaGetLastError());
+    GemmCall g;
+    g.A = w.c1; g.a_cols = d; g.a_rows = (int64_t)batch * 3002; g.a_ld = d; g.a_stride = 2; g.a_kpt = d / GEMM_BK; g.taps = 3;
+    g.M = (int64_t)batch * 1501; g.W = h->wc2; g.w_rows = d; g.n_per_group = d; g.groups = 1;
+    g.bias = h->bc2; g.act = 1; g.resid = w.sb.x; g.out_f32 = w.sb.x; g.ld_f32 = d; g.rowmap = w.map2;
+    SERENC_TRY(launch_gemm(h, g, st));
+  }
+  EmitCtx e;
+  e.mask = layer_mask; e.reduce = reduce; e.n_sel = popcount64(layer_mask);
+  e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
+  e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
+  e.sumT = sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = w.n_keep;
+  SERENC_TRY(run_stack(h, w.sb, sumT, batch, 1500, w.foff, e, st));
+  return 0;
+}
+
+// =================================================================================================
+// diagnostic op-level entry points
+// =================================================================================================
+extern "C" int serenc_op_gemm(serenc_handle* h, const void* a, int64_t m, int64_t k, int64_t a_row_stride, const void* wt, int64_t n,
+                              const float* bias, const float* resid, int act, float* out_f32, void* out_bf16, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmCall g;
+  if (a_row_stride == k || a_row_stride <= 0) {
+    g = linear_call(reinterpret_cast<const bf16*>(a), m, (int)k, reinterpret_cast<const bf16*>(wt), (int)n);
+  } else {
+    // conv view: input rows of C = gcd-compatible channels; k = taps * C, a_row_stride = s * C, s in {1, 2}
+    int taps = 0, C = 0, s = 0;
+    for (int tps = 2; tps <= 4 && !taps; ++tps)
+      for (int ss = 1; ss <= 2; ++ss)
+        if (k % tps == 0 && (k / tps) * ss == a_row_stride) { taps = tps; C = (int)(k / tps); s = ss; break; }
+    if (!taps || C % GEMM_BK) SERENC_FAIL(SERENC_ERR_INVALID, "op_gemm: cannot interpret k=%lld stride=%lld as a conv", (long long)k, (long long)a_row_stride);
+    g.A = reinterpret_cast<const bf16*>(a); g.a_cols = C; g.a_rows = (m - 1) * s + taps; g.a_ld = C; g.a_stride = s;
+    g.a_kpt = C / GEMM_BK; g.taps = taps; g.M = m; g.W = reinterpret_cast<const bf16*>(wt); g.w_rows = n; g.n_per_group = (int)n; g.groups = 1;
+  }
+  g.bias = bias; g.resid = resid; g.act = act; g.out_f32 = out_f32; g.ld_f32 = n; g.out_bf16 = reinterpret_cast<bf16*>(out_bf16); g.ld_bf16 = n;
+  return launch_gemm(h, g, st);
+}
+
+extern "C" int serenc_op_gemm_grouped(serenc_handle* h, const void* x, int64_t rows, int groups, int cg_pad, int taps, const void* wt,
+                                      int n_per_group, const float* bias, int act, float* out_f32, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  if (cg_pad % GEMM_BK) SERENC_FAIL(SERENC_ERR_INVALID, "cg_pad must be a multiple of 64");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  GemmCall g;
+  const int64_t ld = (int64_t)groups * cg_pad;
+  g.A = reinterpret_cast<const bf16*>(x); g.a_cols = ld; g.a_rows = rows; g.a_ld = ld; g.a_stride = 1; g.a_kpt = cg_pad / GEMM_BK; g.taps = taps;
+  g.a_group_stride = cg_pad; g.M = rows - taps + 1; g.W = reinterpret_cast<const bf16*>(wt); g.w_rows = (int64_t)groups * n_per_group;
+  g.n_per_group = n_per_group; g.groups = groups; g.bias = bias; g.act = act; g.out_f32 = out_f32; g.ld_f32 = (int64_t)groups * n_per_group;
+  return launch_gemm(h, g, st);
+}
+
+extern "C" int serenc_op_layernorm(serenc_handle* h, const float* x, int64_t rows, int cols, const float* gamma, const float* beta,
+                                   float eps, int gelu, float* out_f32, void* out_bf16, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  if (!ln_width_ok(cols)) SERENC_FAIL(SERENC_ERR_INVALID, "layernorm: unsupported width %d", cols);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (out_f32) {
+    if (gelu) SERENC_FAIL(SERENC_ERR_INVALID, "layernorm: gelu variant writes bf16 only");
+    SERENC_TRY((launch_ln_t<float, float, false>(x, cols, out_f32, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+  }
+  if (out_bf16) {
+    bf16* o = reinterpret_cast<bf16*>(out_bf16);
+    if (gelu) SERENC_TRY((launch_ln_t<float, bf16, true>(x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+    else SERENC_TRY((launch_ln_t<float, bf16, false>(x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+  }
+  return 0;
+}
+
+extern "C" int serenc_op_attention(serenc_handle* h, const void* qkv, const int64_t* frame_offsets, int batch, int wavlm, int layer,
+                                   const void* hln, void* out, void* scratch_dev, void* stream) {
+  SERENC_TRY(check_ready(h, -1));
+  if (!qkv || !frame_offsets || !out || !scratch_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  if (wavlm && (!h->cfg.wavlm_rel_bias || layer < 0 || layer >= h->cfg.layers || !hln)) SERENC_FAIL(SERENC_ERR_INVALID, "wavlm attention needs a WavLM handle, a layer and hln");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int d = h->cfg.hidden;
+  int32_t* d_off = reinterpret_cast<int32_t*>(scratch_dev);
+  void* hs;
+  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs));
+  int tmax = 0;
+  for (int b = 0; b <= batch; ++b) {
+    reinterpret_cast<int32_t*>(hs)[b] = (int32_t)frame_offsets[b];
+    if (b && frame_offsets[b] - frame_offsets[b - 1] > tmax) tmax = (int)(frame_offsets[b] - frame_offsets[b - 1]);
+  }
+  SERENC_CUDA_OK(cudaMemcpyAsync(d_off, hs, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
+  SERENC_TRY(stage_commit(st));
+  AttnParams p;
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = 3 * d; p.d = d; p.frame_off = d_off; p.out = reinterpret_cast<bf16*>(out);
+  p.scale = 1.0f / sqrtf((float)h->head_dim);
+  p.hln = reinterpret_cast<const bf16*>(hln);
+  const LayerW& l = h->L[wavlm ? layer : 0];
+  p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
+  return launch_attn(h, p, wavlm != 0, tmax, batch, st);
+}

@@ -1,0 +1,185 @@
+"""Thin Python driver over the libserenc C ABI: owns the handle, allocates tensors/workspaces with torch
+(device memory + streams only) and calls the encode entry points. No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .configs import ARCH_WHISPER, ARCH_W2V, EncoderConfig, w2v_num_frames
+
+REDUCE_NONE = 0
+REDUCE_MEAN = 1
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def layer_mask_of(indices: Iterable[int], num_layers: int) -> Tuple[int, List[int]]:
+    """hidden_states indices (negative allowed, as in `hidden_states[-4:]`) -> (bit mask, sorted indices)."""
+    n = num_layers + 1
+    idx = sorted({(i + n) if i < 0 else i for i in indices})
+    for i in idx:
+        if not 0 <= i < n:
+            raise IndexError(f"hidden state index {i} out of range for {n} hidden states")
+    mask = 0
+    for i in idx:
+        mask |= 1 << i
+    return mask, idx
+
+
+class Engine:
+    """One encoder replica on one GPU."""
+
+    def __init__(self, cfg: EncoderConfig, tensors: Dict[str, np.ndarray], device: int | str | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("interspeech_ser_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise RuntimeError("interspeech_ser_b200 runs on CUDA devices only")
+        self.device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device(f"cuda:{self.device_index}")
+        self._lib = _lib.load_library()
+        c = _lib.SerencConfig()
+        c.arch = cfg.arch
+        c.hidden, c.layers, c.heads, c.ffn = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads, cfg.intermediate_size
+        c.conv_dim = cfg.conv_dim[0]
+        c.conv_bias = int(cfg.conv_bias)
+        c.wavlm_rel_bias = int(cfg.family == "wavlm")
+        c.num_buckets, c.max_distance = cfg.num_buckets, cfg.max_bucket_distance
+        c.pos_conv_kernel, c.pos_conv_groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        c.n_mels, c.max_source_positions = cfg.num_mel_bins, cfg.max_source_positions
+        c.layer_norm_eps = cfg.layer_norm_eps
+        if cfg.arch == ARCH_W2V:
+            if cfg.feat_extract_norm != "layer" or not cfg.do_stable_layer_norm:
+                raise NotImplementedError("only feat_extract_norm='layer' + do_stable_layer_norm=True encoders "
+                                          "(the *-large / xlarge / xls-r checkpoints the reference uses) are built")
+            if tuple(cfg.conv_kernel) != (10, 3, 3, 3, 3, 2, 2) or tuple(cfg.conv_stride) != (5, 2, 2, 2, 2, 2, 2):
+                raise NotImplementedError("unsupported feature-encoder geometry")
+        h = C.c_void_p()
+        torch.cuda.init()
+        _lib.check(self._lib.serenc_create(C.byref(c), self.device_index, C.byref(h)))
+        self._h = h
+        try:
+            for name, arr in tensors.items():
+                arr = np.ascontiguousarray(arr, dtype=np.float32)
+                shape = _lib.i64_array(arr.shape if arr.ndim else (1,))
+                _lib.check(self._lib.serenc_load_tensor(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), shape,
+                                                        max(arr.ndim, 1)))
+            _lib.check(self._lib.serenc_finalize(self._h))
+        except Exception:
+            self.close()
+            raise
+        self._tls = threading.local()
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.serenc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        ws = getattr(self._tls, "ws", None)
+        if ws is None or ws.numel() < nbytes:
+            self._tls.ws = None
+            ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+            self._tls.ws = ws
+        return ws
+
+    # ------------------------------------------------------------------ wav2vec2 family
+    def w2v_workspace_bytes(self, lens: Sequence[int]) -> int:
+        out = C.c_size_t()
+        _lib.check(self._lib.serenc_w2v_workspace_bytes(self._h, _lib.i32_array(lens), len(lens), C.byref(out)))
+        return int(out.value)
+
+    def normalize(self, wav: torch.Tensor, starts: Sequence[int], lens: Sequence[int], out_len: int) -> torch.Tensor:
+        """Feature-extractor normalisation on the GPU -> [B, out_len] fp32 (zero right padding)."""
+        B = len(lens)
+        out = torch.empty((B, out_len), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_wav_normalize(self._h, wav.data_ptr(), _lib.i64_array(starts), _lib.i32_array(lens), B,
+                                                      out.data_ptr(), out_len, out_len, _stream_ptr(self.device)))
+        return out
+
+    def encode_w2v(self, wav: torch.Tensor, starts: Sequence[int], lens: Sequence[int], *, normalize: bool,
+                   layers: Iterable[int], reduce: int = REDUCE_NONE, want_frames: bool = True,
+                   want_pooled: bool = False):
+        """Returns (frames | None, pooled | None, frame_offsets[B+1], selected layer indices).
+        frames: [n_sel, sum_T, d] (REDUCE_NONE) or [sum_T, d]; pooled: [n_sel, B, d] or [B, d]."""
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous()
+        B = len(lens)
+        mask, idx = layer_mask_of(layers, self.cfg.num_hidden_layers)
+        T = [w2v_num_frames(n, self.cfg) for n in lens]
+        for b, t in enumerate(T):
+            if t < 1:
+                raise ValueError(f"utterance {b}: {lens[b]} samples is shorter than the 400-sample receptive field")
+        sumT, d = sum(T), self.cfg.hidden_size
+        lead = () if reduce == REDUCE_MEAN else (len(idx),)
+        frames = torch.empty(lead + (sumT, d), dtype=torch.float32, device=self.device) if want_frames else None
+        pooled = torch.empty(lead + (B, d), dtype=torch.float32, device=self.device) if want_pooled else None
+        ws = self._workspace(self.w2v_workspace_bytes(lens))
+        offs = (C.c_int64 * (B + 1))()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_encode_w2v(
+                self._h, wav.data_ptr(), _lib.i64_array(starts), _lib.i32_array(lens), B, int(normalize), mask, reduce,
+                _ptr(frames), _ptr(pooled), offs, ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return frames, pooled, list(offs), idx
+
+    def unpack(self, packed: torch.Tensor, offsets: Sequence[int], t_max: int) -> torch.Tensor:
+        B = len(offsets) - 1
+        out = torch.empty((B, t_max, self.cfg.hidden_size), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_unpack_frames(self._h, packed.data_ptr(), _lib.i64_array(offsets), B, t_max,
+                                                      out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ whisper
+    def logmel(self, wav: torch.Tensor, starts: Sequence[int], lens: Sequence[int]) -> torch.Tensor:
+        B = len(lens)
+        mel = torch.empty((B, self.cfg.num_mel_bins, 3000), dtype=torch.float32, device=self.device)
+        scratch = torch.empty(64 + 40 * B + 64, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_logmel(self._h, wav.data_ptr(), _lib.i64_array(starts), _lib.i32_array(lens), B,
+                                               mel.data_ptr(), scratch.data_ptr(), _stream_ptr(self.device)))
+        return mel
+
+    def whisper_workspace_bytes(self, batch: int) -> int:
+        out = C.c_size_t()
+        _lib.check(self._lib.serenc_whisper_workspace_bytes(self._h, batch, C.byref(out)))
+        return int(out.value)
+
+    def encode_whisper(self, mel: torch.Tensor, *, layers: Iterable[int], reduce: int = REDUCE_NONE,
+                       n_keep: Optional[Sequence[int]] = None, want_frames: bool = True, want_pooled: bool = False):
+        assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
+        if mel.dim() != 3 or mel.shape[1] != self.cfg.num_mel_bins or mel.shape[2] != 3000:
+            # HF WhisperEncoder.forward raises ValueError here (modeling_whisper.py:613-617)
+            raise ValueError(f"Whisper expects the mel input features to be of length 3000, but found {tuple(mel.shape)}. "
+                             "Make sure to pad the input mel features to 3000.")
+        B = mel.shape[0]
+        mask, idx = layer_mask_of(layers, self.cfg.num_hidden_layers)
+        d = self.cfg.hidden_size
+        lead = () if reduce == REDUCE_MEAN else (len(idx),)
+        frames = torch.empty(lead + (B * 1500, d), dtype=torch.float32, device=self.device) if want_frames else None
+        pooled = torch.empty(lead + (B, d), dtype=torch.float32, device=self.device) if want_pooled else None
+        ws = self._workspace(self.whisper_workspace_bytes(B))
+        keep = _lib.i32_array(n_keep) if n_keep is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_encode_whisper(self._h, mel.data_ptr(), B, mask, reduce, keep, _ptr(frames),
+                                                       _ptr(pooled), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return frames, pooled, idx

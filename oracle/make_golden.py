@@ -1,0 +1,288 @@
+"""Pins the oracle against the reference implementation (HuggingFace transformers) and mints golden fixtures.
+
+Run in the build container (needs `transformers`; not needed at test time):
+
+    python oracle/make_golden.py            # tiny configs + kernel-level KATs     (seconds)
+    python oracle/make_golden.py --full     # + full-size WavLM-large / Whisper-large-v3 / HuBERT-xl / XLS-R  (minutes)
+
+For every case the SAME canonical weights (interspeech_ser_b200.weights.random_init(cfg, seed) — regenerated
+from the seed at test time, never stored) are loaded into the HF module; HF's fp32 CPU forward is the reference
+result. The script asserts oracle == HF to fp32 round-off and stores HF's numbers under tests/golden/.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from interspeech_ser_b200 import configs as C  # noqa: E402
+from interspeech_ser_b200.weights import random_init  # noqa: E402
+from oracle import ssl_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+WAVE_STD = 0.0886  # MSP-Podcast corpus std (benchmark/model/cat_ser/7/train_norm_stat.pkl in the reference)
+
+
+def synth_wave(seed: int, n: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal(n, dtype=np.float32) * np.float32(WAVE_STD)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# canonical -> HF
+# ------------------------------------------------------------------------------------------------
+def hf_model(cfg: C.EncoderConfig, w):
+    import transformers as tr
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    sd = {}
+    if cfg.family == "whisper":
+        hc = tr.WhisperConfig(d_model=cfg.hidden_size, encoder_layers=cfg.num_hidden_layers,
+                              encoder_attention_heads=cfg.num_attention_heads, encoder_ffn_dim=cfg.intermediate_size,
+                              num_mel_bins=cfg.num_mel_bins, max_source_positions=cfg.max_source_positions,
+                              decoder_layers=1, decoder_attention_heads=cfg.num_attention_heads, decoder_ffn_dim=64,
+                              vocab_size=128, activation_function="gelu", dropout=0.0, attention_dropout=0.0,
+                              activation_dropout=0.0)
+        from transformers.models.whisper.modeling_whisper import WhisperEncoder
+
+        m = WhisperEncoder(hc).eval()
+        for n in ("conv1", "conv2"):
+            sd[f"{n}.weight"], sd[f"{n}.bias"] = t(w[f"{n}.weight"]), t(w[f"{n}.bias"])
+        sd["embed_positions.weight"] = t(w["embed_positions"])
+        for i in range(cfg.num_hidden_layers):
+            b = f"layers.{i}."
+            sd[b + "self_attn_layer_norm.weight"], sd[b + "self_attn_layer_norm.bias"] = t(w[f"layer{i}.ln1.weight"]), t(w[f"layer{i}.ln1.bias"])
+            for s, n in (("q", "q_proj"), ("k", "k_proj"), ("v", "v_proj"), ("o", "out_proj")):
+                sd[b + f"self_attn.{n}.weight"] = t(w[f"layer{i}.{s}.weight"])
+                if s != "k":
+                    sd[b + f"self_attn.{n}.bias"] = t(w[f"layer{i}.{s}.bias"])
+            sd[b + "final_layer_norm.weight"], sd[b + "final_layer_norm.bias"] = t(w[f"layer{i}.ln2.weight"]), t(w[f"layer{i}.ln2.bias"])
+            for n in ("fc1", "fc2"):
+                sd[b + f"{n}.weight"], sd[b + f"{n}.bias"] = t(w[f"layer{i}.{n}.weight"]), t(w[f"layer{i}.{n}.bias"])
+        sd["layer_norm.weight"], sd["layer_norm.bias"] = t(w["final_ln.weight"]), t(w["final_ln.bias"])
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("k_proj.bias" in k for k in missing), (missing, unexpected)
+        return m
+
+    common = dict(hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
+                  num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
+                  conv_dim=list(cfg.conv_dim), conv_kernel=list(cfg.conv_kernel), conv_stride=list(cfg.conv_stride),
+                  conv_bias=cfg.conv_bias, feat_extract_norm="layer", do_stable_layer_norm=True,
+                  num_conv_pos_embeddings=cfg.num_conv_pos_embeddings,
+                  num_conv_pos_embedding_groups=cfg.num_conv_pos_embedding_groups, hidden_dropout=0.0,
+                  attention_dropout=0.0, activation_dropout=0.0, feat_proj_dropout=0.0, layerdrop=0.0,
+                  layer_norm_eps=cfg.layer_norm_eps, hidden_act="gelu", feat_extract_activation="gelu")
+    if cfg.family == "wavlm":
+        m = tr.WavLMModel(tr.WavLMConfig(num_buckets=cfg.num_buckets, max_bucket_distance=cfg.max_bucket_distance, **common))
+    elif cfg.family == "hubert":
+        m = tr.HubertModel(tr.HubertConfig(feat_proj_layer_norm=True, **common))
+    else:
+        m = tr.Wav2Vec2Model(tr.Wav2Vec2Config(**common))
+    m = m.eval()
+    for i in range(7):
+        b = f"feature_extractor.conv_layers.{i}."
+        sd[b + "conv.weight"] = t(w[f"conv{i}.weight"])
+        if cfg.conv_bias:
+            sd[b + "conv.bias"] = t(w[f"conv{i}.bias"])
+        sd[b + "layer_norm.weight"], sd[b + "layer_norm.bias"] = t(w[f"conv{i}.ln.weight"]), t(w[f"conv{i}.ln.bias"])
+    sd["feature_projection.layer_norm.weight"], sd["feature_projection.layer_norm.bias"] = t(w["featproj.ln.weight"]), t(w["featproj.ln.bias"])
+    sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"] = t(w["featproj.weight"]), t(w["featproj.bias"])
+    pw = t(w["posconv.weight"])
+    # weight_norm(dim=2): choose g = ||W[:, :, k]|| and v = W so that g * v / ||v|| == W
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = pw.pow(2).sum(dim=(0, 1), keepdim=True).sqrt()
+    sd["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = pw
+    sd["encoder.pos_conv_embed.conv.bias"] = t(w["posconv.bias"])
+    for i in range(cfg.num_hidden_layers):
+        b = f"encoder.layers.{i}."
+        sd[b + "layer_norm.weight"], sd[b + "layer_norm.bias"] = t(w[f"layer{i}.ln1.weight"]), t(w[f"layer{i}.ln1.bias"])
+        for s, n in (("q", "q_proj"), ("k", "k_proj"), ("v", "v_proj"), ("o", "out_proj")):
+            sd[b + f"attention.{n}.weight"], sd[b + f"attention.{n}.bias"] = t(w[f"layer{i}.{s}.weight"]), t(w[f"layer{i}.{s}.bias"])
+        sd[b + "final_layer_norm.weight"], sd[b + "final_layer_norm.bias"] = t(w[f"layer{i}.ln2.weight"]), t(w[f"layer{i}.ln2.bias"])
+        sd[b + "feed_forward.intermediate_dense.weight"], sd[b + "feed_forward.intermediate_dense.bias"] = t(w[f"layer{i}.fc1.weight"]), t(w[f"layer{i}.fc1.bias"])
+        sd[b + "feed_forward.output_dense.weight"], sd[b + "feed_forward.output_dense.bias"] = t(w[f"layer{i}.fc2.weight"]), t(w[f"layer{i}.fc2.bias"])
+        if cfg.family == "wavlm":
+            sd[b + "attention.gru_rel_pos_linear.weight"], sd[b + "attention.gru_rel_pos_linear.bias"] = t(w[f"layer{i}.gru.weight"]), t(w[f"layer{i}.gru.bias"])
+            sd[b + "attention.gru_rel_pos_const"] = t(w[f"layer{i}.gru.const"]).view(1, -1, 1, 1)
+    if cfg.family == "wavlm":
+        sd["encoder.layers.0.attention.rel_attn_embed.weight"] = t(w["rel_attn_embed"])
+    sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"] = t(w["final_ln.weight"]), t(w["final_ln.bias"])
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(("masked_spec_embed" in k) for k in missing), missing
+    return m
+
+
+def pooled_all(hs) -> np.ndarray:
+    return np.stack([h.reshape(-1, h.shape[-1]).mean(dim=0).numpy() for h in hs])
+
+
+def check_close(name, a, b, atol):
+    err = float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+    print(f"    {name}: max |oracle - HF| = {err:.3e}")
+    assert err <= atol, f"{name}: oracle deviates from HF by {err} > {atol}"
+    return err
+
+
+def golden_w2v(cfg_name: str, lengths, seed=0, atol=2e-4):
+    import transformers as tr
+
+    cfg = C.get_config(cfg_name)
+    print(f"[{cfg.name}] generating weights (seed {seed})")
+    w = random_init(cfg, seed)
+    m = hf_model(cfg, w)
+    fe = tr.Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True, return_attention_mask=True)
+    out = {"lengths": np.asarray(lengths, dtype=np.int64), "seed": np.int64(seed), "wave_seed_base": np.int64(7)}
+    for j, n in enumerate(lengths):
+        wav = synth_wave(7 + j, n)
+        t0 = time.time()
+        inputs = fe(wav, sampling_rate=16000, return_tensors="pt", padding=True)
+        np.testing.assert_allclose(inputs["input_values"][0].numpy(), O.normalize_waveform(wav), atol=1e-5)
+        with torch.no_grad():
+            res = m(**inputs, output_hidden_states=True)
+        hs_hf = [h[0] for h in res.hidden_states]
+        t_hf = time.time() - t0
+        hs_or = O.w2v_hidden_states(cfg, w, wav)
+        assert len(hs_hf) == len(hs_or) == cfg.num_hidden_layers + 1
+        assert hs_hf[0].shape[0] == O.w2v_num_frames(n)
+        print(f"  len {n}: T={hs_hf[0].shape[0]}  (HF forward {t_hf:.2f}s)")
+        scale = max(float(h.abs().max()) for h in hs_hf)
+        worst = max(float((a - b).abs().max()) for a, b in zip(hs_or, hs_hf))
+        print(f"    hidden states: max |oracle - HF| = {worst:.3e} (max |HF| = {scale:.2f})")
+        assert worst <= atol * max(1.0, scale), worst
+        out[f"pooled_{j}"] = pooled_all(hs_hf).astype(np.float32)          # [L+1, d] masked mean of every hidden state
+        out[f"last_{j}"] = hs_hf[-1][:4].numpy().astype(np.float32)         # first 4 frames of last_hidden_state
+        out[f"meanlast4_pooled_{j}"] = torch.mean(torch.stack(hs_hf[-4:]), 0).mean(0).numpy().astype(np.float32)
+    path = os.path.join(GOLDEN, cfg.name.replace("/", "__") + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path}")
+
+
+def golden_whisper(cfg_name: str, lengths, seed=0, atol=2e-4, mel_stride=25):
+    import transformers as tr
+
+    cfg = C.get_config(cfg_name)
+    print(f"[{cfg.name}] generating weights (seed {seed})")
+    w = random_init(cfg, seed)
+    m = hf_model(cfg, w)
+    fe = tr.WhisperFeatureExtractor(feature_size=cfg.num_mel_bins)
+    np.testing.assert_allclose(fe.mel_filters, w["mel_filters"], atol=1e-7)
+    out = {"lengths": np.asarray(lengths, dtype=np.int64), "seed": np.int64(seed), "wave_seed_base": np.int64(7),
+           "mel_stride": np.int64(mel_stride)}
+    for j, n in enumerate(lengths):
+        wav = synth_wave(7 + j, n)
+        mel_hf = fe(wav, sampling_rate=16000, return_tensors="pt")["input_features"]
+        mel_or = O.whisper_log_mel(w, wav)
+        check_close(f"len {n} log-mel", mel_or.numpy(), mel_hf[0].numpy(), 1e-4)
+        t0 = time.time()
+        with torch.no_grad():
+            res = m(mel_hf, output_hidden_states=True)
+        hs_hf = [h[0] for h in res.hidden_states]
+        print(f"  len {n}: HF encoder forward {time.time() - t0:.2f}s")
+        hs_or = O.whisper_hidden_states(cfg, w, mel_hf[0])
+        assert len(hs_hf) == len(hs_or) == cfg.num_hidden_layers + 1
+        scale = max(float(h.abs().max()) for h in hs_hf)
+        worst = max(float((a - b).abs().max()) for a, b in zip(hs_or, hs_hf))
+        print(f"    hidden states: max |oracle - HF| = {worst:.3e} (max |HF| = {scale:.2f})")
+        assert worst <= atol * max(1.0, scale), worst
+        keep = O.whisper_keep_frames(n, cfg.hidden_size)
+        out[f"mel_sub_{j}"] = mel_hf[0][:, ::mel_stride].numpy().astype(np.float32)
+        out[f"pooled_{j}"] = np.stack([h[:keep].mean(0).numpy() for h in hs_hf]).astype(np.float32)
+        out[f"keep_{j}"] = np.int64(keep)
+        out[f"last_{j}"] = hs_hf[-1][:4].numpy().astype(np.float32)
+    path = os.path.join(GOLDEN, cfg.name.replace("/", "__") + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path}")
+
+
+def golden_logmel_signals():
+    """Log-mel KATs on structured signals (SURVEY §8c iv): silence, impulse, sines, noise; 1 s / 30 s / 31 s."""
+    import transformers as tr
+
+    fe = tr.WhisperFeatureExtractor(feature_size=128)
+    w = {"mel_filters": fe.mel_filters.astype(np.float32)}
+    sigs = logmel_signals()
+    out = {}
+    for name, x in sigs.items():
+        mel_hf = fe(x, sampling_rate=16000, return_tensors="pt")["input_features"][0].numpy()
+        mel_or = O.whisper_log_mel(w, x).numpy()
+        check_close(f"logmel[{name}]", mel_or, mel_hf, 1e-4)
+        out[name] = mel_hf[:, ::25].astype(np.float32)
+    np.savez_compressed(os.path.join(GOLDEN, "logmel_signals.npz"), **out)
+    print("  wrote logmel_signals.npz")
+
+
+def logmel_signals():
+    sr = 16000
+    t1 = np.arange(sr, dtype=np.float64) / sr
+    t30 = np.arange(30 * sr, dtype=np.float64) / sr
+    imp = np.zeros(5 * sr, dtype=np.float32)
+    imp[12345] = 1.0
+    return {
+        "silence_2s": np.zeros(2 * sr, dtype=np.float32),
+        "impulse_5s": imp,
+        "sine440_1s": np.sin(2 * np.pi * 440.0 * t1).astype(np.float32),
+        "sine7999_30s": (0.5 * np.sin(2 * np.pi * 7999.0 * t30)).astype(np.float32),
+        "noise_30s": synth_wave(11, 30 * sr),
+        "noise_31s": synth_wave(12, 31 * sr),
+        "noise_1s": synth_wave(13, sr),
+    }
+
+
+def golden_buckets():
+    from transformers.models.wavlm.modeling_wavlm import WavLMAttention
+
+    att = WavLMAttention(embed_dim=128, num_heads=2, num_buckets=320, max_distance=800)
+    rel = torch.arange(-1499, 1500, dtype=torch.long)[None, :]
+    hf = att._relative_positions_bucket(rel)[0].numpy()
+    mine = O.wavlm_bucket(rel)[0].numpy()
+    assert np.array_equal(hf, mine)
+    kat = {-1: 1, 1: 161, 79: 239, 80: 240, 81: 240, 100: 247, 200: 271, 400: 295, -400: 135}
+    for dlt, b in kat.items():
+        assert hf[dlt + 1499] == b, (dlt, hf[dlt + 1499], b)
+    np.savez_compressed(os.path.join(GOLDEN, "wavlm_buckets.npz"), delta=rel[0].numpy(), bucket=hf.astype(np.int32))
+    print("  wrote wavlm_buckets.npz (HF _relative_positions_bucket for delta in [-1499, 1499])")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also full-size architectures (minutes, GBs of RAM)")
+    ap.add_argument("--only", default="", help="comma-separated config names")
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    only = [s for s in args.only.split(",") if s]
+
+    def want(n):
+        return not only or n in only
+
+    if want("kats"):
+        golden_buckets()
+        golden_logmel_signals()
+    tiny_lengths = [400, 401, 719, 720, 4001, 17777, 32000]
+    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120"):
+        if want(name):
+            golden_w2v(name, tiny_lengths)
+    for name in ("tiny/whisper", "tiny/whisper128"):
+        if want(name):
+            golden_whisper(name, [16000, 80000, 480000, 496000])
+    if args.full:
+        if want("microsoft/wavlm-large"):
+            golden_w2v("microsoft/wavlm-large", [4001, 64000, 192000], atol=5e-4)
+        if want("openai/whisper-large-v3"):
+            golden_whisper("openai/whisper-large-v3", [64000], atol=5e-4)
+        if want("facebook/hubert-xlarge-ls960-ft"):
+            golden_w2v("facebook/hubert-xlarge-ls960-ft", [64000], atol=5e-4)
+        if want("facebook/wav2vec2-xls-r-2b"):
+            golden_w2v("facebook/wav2vec2-xls-r-2b", [64000], atol=5e-4)
+
+
+if __name__ == "__main__":
+    main()
