@@ -225,9 +225,9 @@ def cmd_model(name, lens=None, full_layers=True):
         cos = [float(torch.nn.functional.cosine_similarity(pooled[i, b], hs[i].mean(0), dim=0)) for i in range(L + 1)]
         show = list(range(L + 1)) if L <= 4 else [0, 1, 2, L // 2, L - 1, L]
         print(f"  utt{b} len={lens[b]} T={e - s}: " + " ".join(f"hs{i}:err={errs[i]:.2e},cos={cos[i]:.5f}" for i in show), flush=True)
-    fm, pm, _, _ = eng.encode_w2v(wav, starts, lens, normalize=True, layers=[-4, -3, -2, -1], reduce=REDUCE_MEAN, want_frames=True, want_pooled=True)
+    fm, pm, _, _ = eng.encode_w2v(wav, starts, lens, normalize=True, layers=list(range(max(0, L - 3), L + 1)), reduce=REDUCE_MEAN, want_frames=True, want_pooled=True)
     torch.cuda.synchronize()
-    ref = frames[-4:].mean(0)
+    ref = frames[max(0, L - 3):].mean(0)
     print(f"  mean-last-4 frames vs own hidden states: {rel_err(fm.cpu(), ref):.2e}", flush=True)
 
 
