@@ -152,6 +152,32 @@ int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int batch, uin
                           const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
 
+/* ---- launch accounting / per-kernel-class device timing (used by bench.py for the roofline numbers) ---- */
+
+typedef enum {
+  SERENC_PROF_GEMM_LINEAR = 0, /* other Linear layers (feature projection) (tcgen05)           */
+  SERENC_PROF_GEMM_CONV = 1,   /* conv1..6 / Whisper conv stem as implicit GEMMs (tcgen05)     */
+  SERENC_PROF_GEMM_POSCONV = 2,/* grouped positional conv as implicit GEMM (tcgen05)           */
+  SERENC_PROF_ATTENTION = 3,
+  SERENC_PROF_LAYERNORM = 4,
+  SERENC_PROF_CONV0 = 5,
+  SERENC_PROF_POOL = 6,        /* hidden-state accumulation + masked mean pooling               */
+  SERENC_PROF_LOGMEL = 7,
+  SERENC_PROF_MISC = 8,
+  SERENC_PROF_GEMM_QKV = 9,    /* fused q|k|v projection, bias, bf16 out                        */
+  SERENC_PROF_GEMM_OUT = 10,   /* attention out projection, bias + fp32 residual                */
+  SERENC_PROF_GEMM_FC1 = 11,   /* FFN up projection, bias + exact GELU, bf16 out                */
+  SERENC_PROF_GEMM_FC2 = 12,   /* FFN down projection, bias + fp32 residual                     */
+  SERENC_PROF_NUM_CLASSES = 13
+} serenc_prof_class;
+
+/* Kernel launches (incl. memset nodes) issued through this handle since creation. */
+int64_t serenc_launch_count(const serenc_handle* h);
+/* enable != 0: bracket every launch with CUDA events on its stream (single-threaded use); clears old records. */
+int serenc_set_profiling(serenc_handle* h, int enable);
+/* Synchronises and sums, per class, device milliseconds / algorithmic FLOPs / algorithmic bytes / launches. */
+int serenc_get_profile(serenc_handle* h, int n_classes, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* ---- diagnostic entry points (op-level known-answer tests; not needed by an integrator) ------------ */
 
 /* out = epilogue(A[M,K] * W[N,K]^T): bf16 operands, fp32 accumulate. a_row_stride (elements) may be smaller

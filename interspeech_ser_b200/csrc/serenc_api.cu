@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <array>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <set>
@@ -97,7 +98,42 @@ struct serenc_handle {
 
   std::mutex mu;
   std::map<std::array<uint64_t, 8>, CUtensorMap> tmaps;
+
+  // launch accounting / optional per-class device timing (bench.py's roofline numbers)
+  std::atomic<long long> launches{0};
+  bool prof = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
+  std::vector<ProfRec> recs;
 };
+
+namespace {
+// Counts kernel launches; when profiling is on, brackets them with CUDA events on the launching stream.
+struct ProfScope {
+  serenc_handle* h;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(serenc_handle* h_, int cls, int n_launches, double flops, double bytes, cudaStream_t st_) : h(h_), st(st_) {
+    h->launches += n_launches;
+    if (h->prof) {
+      serenc_handle::ProfRec r;
+      r.cls = cls; r.flops = flops; r.bytes = bytes; r.n = n_launches;
+      if (cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess) {
+        cudaEventRecord(r.a, st);
+        std::lock_guard<std::mutex> lk(h->mu);
+        idx = (int)h->recs.size();
+        h->recs.push_back(r);
+      }
+    }
+  }
+  ~ProfScope() {
+    if (idx >= 0) {
+      cudaEvent_t b;
+      { std::lock_guard<std::mutex> lk(h->mu); b = h->recs[idx].b; }
+      cudaEventRecord(b, st);
+    }
+  }
+};
+}  // namespace
 
 namespace {
 
@@ -206,6 +242,8 @@ struct GemmCall {
   int64_t ld_bf16 = 0;
   const int32_t* rowmap = nullptr;
   int act = 0;
+  int prof_cls = SERENC_PROF_GEMM_LINEAR;
+  double alg_flops = -1.0;    // algorithmic FLOPs (valid rows, unpadded K); < 0: 2*M*N*K of the launch
 };
 
 template <int BN>
@@ -247,6 +285,11 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.groups;
   if (tiles <= 0) return 0;
   const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  const double flops = c.alg_flops >= 0 ? c.alg_flops : 2.0 * (double)c.M * c.n_per_group * c.groups * p.num_kb * GEMM_BK;
+  const double bytes = 2.0 * ((double)c.M * p.num_kb * GEMM_BK / (c.taps > 1 ? c.taps : 1) * c.groups / (c.groups > 1 ? c.groups : 1) +
+                              (double)c.w_rows * p.num_kb * GEMM_BK) +
+                       (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
+  ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
@@ -286,11 +329,12 @@ GemmCall linear_call(const bf16* A, int64_t M, int K, const bf16* W, int N) {
 // LayerNorm launch
 // ---------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut, bool GELU>
-int launch_ln_t(const TIn* in, int64_t ld_in, TOut* out, int64_t ld_out, const float* g, const float* b, int64_t rows,
+int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64_t ld_out, const float* g, const float* b, int64_t rows,
                 int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st) {
   if (rows <= 0) return 0;
   const int nv = cols / 128;
   const dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+  ProfScope ps(h, SERENC_PROF_LAYERNORM, 1, 0.0, (double)rows * cols * (sizeof(TIn) + sizeof(TOut)), st);
 #define SERENC_LN_CASE(NV)                                                                                       \
   case NV:                                                                                                       \
     layernorm_rows_kernel<NV, TIn, TOut, GELU><<<grid, block, 0, st>>>(in, ld_in, out, ld_out, g, b, rows, in_map, \
@@ -336,8 +380,9 @@ int launch_attn_hd(const AttnParams& p, bool wavlm, int tmax, int heads, int bat
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, cudaStream_t st) {
+int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, double alg_flops, cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
+  ProfScope ps(h, SERENC_PROF_ATTENTION, 1, alg_flops, 0.0, st);
   switch (h->head_dim) {
     case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
     case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
@@ -450,6 +495,34 @@ extern "C" int serenc_wavlm_bucket(int delta, int num_buckets, int max_distance)
 
 extern "C" const char* serenc_last_error(void) { return g_err; }
 extern "C" const char* serenc_version(void) { return "serenc 0.1 (sm_100a; tcgen05 GEMM, mma.sync attention)"; }
+
+extern "C" int64_t serenc_launch_count(const serenc_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
+
+extern "C" int serenc_set_profiling(serenc_handle* h, int enable) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  SERENC_CUDA_OK(cudaSetDevice(h->device));
+  SERENC_CUDA_OK(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (auto& r : h->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->recs.clear();
+  h->prof = enable != 0;
+  return 0;
+}
+
+extern "C" int serenc_get_profile(serenc_handle* h, int n_classes, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!h || !ms || !flops || !bytes || !launches) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  SERENC_CUDA_OK(cudaSetDevice(h->device));
+  SERENC_CUDA_OK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) { ms[i] = flops[i] = bytes[i] = 0.0; launches[i] = 0; }
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (auto& r : h->recs) {
+    if (r.cls < 0 || r.cls >= n_classes) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) continue;
+    ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += r.n;
+  }
+  return 0;
+}
 
 // =================================================================================================
 // lifecycle
@@ -739,23 +812,25 @@ struct EmitCtx {
   const int32_t* n_keep_dev;
 };
 
-int pool_launch(const float* x, int d, int batch, const int32_t* foff, const int32_t* n_keep, float* out, cudaStream_t st) {
+int pool_launch(serenc_handle* h, const float* x, int64_t sumT, int d, int batch, const int32_t* foff, const int32_t* n_keep, float* out, cudaStream_t st) {
   const dim3 grid(ceil_div(d, 128), batch);
+  ProfScope ps(h, SERENC_PROF_POOL, 1, 0.0, (double)sumT * d * 4 + (double)batch * d * 4, st);
   masked_mean_pool_kernel<<<grid, 256, 0, st>>>(x, d, foff, n_keep, out);
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int emit_hidden(EmitCtx& e, int idx, const float* src, cudaStream_t st) {
+int emit_hidden(serenc_handle* h, EmitCtx& e, int idx, const float* src, cudaStream_t st) {
   if (!((e.mask >> idx) & 1ull)) return 0;
   const int64_t n = e.sumT * e.d;
   if (e.reduce == SERENC_REDUCE_NONE) {
     if (e.frames_out)
       SERENC_CUDA_OK(cudaMemcpyAsync(e.frames_out + (int64_t)e.sel * n, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (e.pooled_out)
-      SERENC_TRY(pool_launch(src, e.d, e.batch, e.frame_off_dev, e.n_keep_dev, e.pooled_out + (int64_t)e.sel * e.batch * e.d, st));
+      SERENC_TRY(pool_launch(h, src, e.sumT, e.d, e.batch, e.frame_off_dev, e.n_keep_dev, e.pooled_out + (int64_t)e.sel * e.batch * e.d, st));
   } else {
     const int64_t n4 = n / 4;
+    ProfScope ps(h, SERENC_PROF_POOL, 1, 0.0, (double)n * (e.first ? 8 : 12), st);
     accum_scaled_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(e.acc, src, n4, 1.0f / (float)e.n_sel, e.first ? 1 : 0);
     SERENC_CUDA_OK(cudaGetLastError());
     e.first = false;
@@ -777,16 +852,16 @@ struct StackBufs {
 // WavLMEncoderLayerStableLayerNorm / Wav2Vec2EncoderLayerStableLayerNorm / WhisperEncoderLayer
 // (HF modeling_wavlm.py:339-373, :450-522; modeling_whisper.py:361-414).
 int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int tmax, const int32_t* frame_off_dev,
-              EmitCtx& e, cudaStream_t st) {
+              double attn_flops, EmitCtx& e, cudaStream_t st) {
   const serenc_config& c = h->cfg;
   const int d = c.hidden;
-  SERENC_TRY(emit_hidden(e, 0, b.x, st));
+  SERENC_TRY(emit_hidden(h, e, 0, b.x, st));
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = h->L[li];
-    SERENC_TRY((launch_ln_t<float, bf16, false>(b.x, d, b.hln, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+    SERENC_TRY((launch_ln_t<float, bf16, false>(h, b.x, d, b.hln, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
     {
       GemmCall g = linear_call(b.hln, sumT, d, l.w_qkv, 3 * d);
-      g.bias = l.b_qkv; g.out_bf16 = b.qkv; g.ld_bf16 = 3 * d;
+      g.bias = l.b_qkv; g.out_bf16 = b.qkv; g.ld_bf16 = 3 * d; g.prof_cls = SERENC_PROF_GEMM_QKV;
       SERENC_TRY(launch_gemm(h, g, st));
     }
     {
@@ -794,30 +869,30 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
       p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
-      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, st));
+      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, attn_flops, st));
     }
     {
       GemmCall g = linear_call(b.att, sumT, d, l.w_o, d);
-      g.bias = l.b_o; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d;
+      g.bias = l.b_o; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d; g.prof_cls = SERENC_PROF_GEMM_OUT;
       SERENC_TRY(launch_gemm(h, g, st));
     }
-    SERENC_TRY((launch_ln_t<float, bf16, false>(b.x, d, b.hln, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+    SERENC_TRY((launch_ln_t<float, bf16, false>(h, b.x, d, b.hln, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
     {
       GemmCall g = linear_call(b.hln, sumT, d, l.w_fc1, c.ffn);
-      g.bias = l.b_fc1; g.act = 1; g.out_bf16 = b.ffn; g.ld_bf16 = c.ffn;
+      g.bias = l.b_fc1; g.act = 1; g.out_bf16 = b.ffn; g.ld_bf16 = c.ffn; g.prof_cls = SERENC_PROF_GEMM_FC1;
       SERENC_TRY(launch_gemm(h, g, st));
     }
     {
       GemmCall g = linear_call(b.ffn, sumT, c.ffn, l.w_fc2, d);
-      g.bias = l.b_fc2; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d;
+      g.bias = l.b_fc2; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d; g.prof_cls = SERENC_PROF_GEMM_FC2;
       SERENC_TRY(launch_gemm(h, g, st));
     }
-    if (li + 1 < c.layers) SERENC_TRY(emit_hidden(e, li + 1, b.x, st));
+    if (li + 1 < c.layers) SERENC_TRY(emit_hidden(h, e, li + 1, b.x, st));
   }
-  SERENC_TRY((launch_ln_t<float, float, false>(b.x, d, b.xf, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
-  SERENC_TRY(emit_hidden(e, c.layers, b.xf, st));
+  SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.xf, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+  SERENC_TRY(emit_hidden(h, e, c.layers, b.xf, st));
   if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
-    SERENC_TRY(pool_launch(e.acc, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
+    SERENC_TRY(pool_launch(h, e.acc, sumT, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
   return 0;
 }
 
@@ -1022,6 +1097,7 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     SERENC_CUDA_OK(cudaMemcpyAsync(w.r6, hr, sz_r, cudaMemcpyHostToDevice, st));
     SERENC_TRY(stage_commit(st));
     const int64_t nthreads = p.sumT > p.mpos ? p.sumT : p.mpos;
+    ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, 0.0, st);
     w2v_plan_kernel<<<(unsigned)ceil_div64(nthreads, 256), 256, 0, st>>>(w.foff, w.r6, batch, p.pad, p.sumT, p.mpos, w.fp_gather, w.gap_row, w.pos_rowmap);
     SERENC_CUDA_OK(cudaGetLastError());
   }
@@ -1029,12 +1105,18 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   // ---- feature encoder: conv0 (+norm stats) then conv1..6 as implicit GEMMs, each followed by LN + GELU ----
   {
     if (normalize) {
+      double nsamp = 0;
+      for (int b = 0; b < batch; ++b) nsamp += sample_len[b];
+      ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, 8.0 * nsamp, st);
       wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, w.utts, w.stats);
       SERENC_CUDA_OK(cudaGetLastError());
     }
     int slot_max = 0;
     for (int b = 0; b < batch; ++b) slot_max = slot_max > ((p.T[6][b] + 2) << 6) ? slot_max : ((p.T[6][b] + 2) << 6);
     const dim3 grid(ceil_div(slot_max, CONV0_TILE), batch);
+    double t0sum = 0, nsamp0 = 0;
+    for (int b = 0; b < batch; ++b) { t0sum += p.T[0][b]; nsamp0 += sample_len[b]; }
+    ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, 4.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
     conv0_ln_gelu_kernel<<<grid, 256, 0, st>>>(wav_dev, w.utts, normalize ? w.stats : nullptr, h->conv0_w,
                                                c.conv_bias ? h->conv_b[0] : nullptr, h->conv_g[0], h->conv_be[0], w.cbuf0);
     SERENC_CUDA_OK(cudaGetLastError());
@@ -1047,12 +1129,14 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     g.M = p.rows[k]; g.W = h->conv_w[k]; g.w_rows = C; g.n_per_group = C; g.groups = 1;
     g.bias = c.conv_bias ? h->conv_b[k] : nullptr;
     g.out_bf16 = cout; g.ld_bf16 = C;
+    g.prof_cls = SERENC_PROF_GEMM_CONV;
+    { double tk = 0; for (int b = 0; b < batch; ++b) tk += p.T[k][b]; g.alg_flops = 2.0 * tk * C * C * W2V_K[k]; }
     SERENC_TRY(launch_gemm(h, g, st));
-    SERENC_TRY((launch_ln_t<bf16, bf16, true>(cout, C, cout, C, h->conv_g[k], h->conv_be[k], p.rows[k], C, nullptr, nullptr, 1e-5f, st)));
+    SERENC_TRY((launch_ln_t<bf16, bf16, true>(h, cout, C, cout, C, h->conv_g[k], h->conv_be[k], p.rows[k], C, nullptr, nullptr, 1e-5f, st)));
     bf16* t = cin; cin = cout; cout = t;
   }
   // ---- feature projection: LN(512) over the valid frames (gathered into the packed layout) -> Linear(512 -> d) ----
-  SERENC_TRY((launch_ln_t<bf16, bf16, false>(cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
+  SERENC_TRY((launch_ln_t<bf16, bf16, false>(h, cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
   {
     GemmCall g = linear_call(w.featln, p.sumT, C, h->fp_w, d);
     g.bias = h->fp_b; g.out_f32 = w.sb.x; g.ld_f32 = d;
@@ -1061,15 +1145,20 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   // ---- positional conv embedding: x += gelu(grouped_conv(x) + b) ----
   {
     const int64_t ld_pos = (int64_t)c.pos_conv_groups * h->pos_cg_pad;
-    SERENC_CUDA_OK(cudaMemsetAsync(w.posin, 0, (size_t)p.rgap * ld_pos * sizeof(bf16), st));
-    const int64_t nthr = p.sumT * (d / 4);
-    scatter_posconv_in_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(w.sb.x, p.sumT, d, h->pos_cg, h->pos_cg_pad, w.gap_row, w.posin, ld_pos);
-    SERENC_CUDA_OK(cudaGetLastError());
+    {
+      const int64_t nthr = p.sumT * (d / 4);
+      ProfScope ps(h, SERENC_PROF_MISC, 2, 0.0, (double)p.sumT * d * 6, st);
+      SERENC_CUDA_OK(cudaMemsetAsync(w.posin, 0, (size_t)p.rgap * ld_pos * sizeof(bf16), st));
+      scatter_posconv_in_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(w.sb.x, p.sumT, d, h->pos_cg, h->pos_cg_pad, w.gap_row, w.posin, ld_pos);
+      SERENC_CUDA_OK(cudaGetLastError());
+    }
     GemmCall g;
     g.A = w.posin; g.a_cols = ld_pos; g.a_rows = p.rgap; g.a_ld = ld_pos; g.a_stride = 1; g.a_kpt = h->pos_cg_pad / GEMM_BK;
     g.taps = c.pos_conv_kernel; g.a_group_stride = h->pos_cg_pad;
     g.M = p.mpos; g.W = h->pos_w; g.w_rows = d; g.n_per_group = h->pos_cg; g.groups = c.pos_conv_groups;
     g.bias = h->pos_b; g.act = 1; g.resid = w.sb.x; g.out_f32 = w.sb.x; g.ld_f32 = d; g.rowmap = w.pos_rowmap;
+    g.prof_cls = SERENC_PROF_GEMM_POSCONV;
+    g.alg_flops = 2.0 * (double)p.sumT * d * h->pos_cg * c.pos_conv_kernel;
     SERENC_TRY(launch_gemm(h, g, st));
   }
   // ---- transformer stack ----
@@ -1078,7 +1167,9 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
   e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
   e.sumT = p.sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = nullptr;
-  SERENC_TRY(run_stack(h, w.sb, p.sumT, batch, p.tmax, w.foff, e, st));
+  double attn_flops = 0.0;
+  for (int b = 0; b < batch; ++b) attn_flops += 4.0 * (double)p.T[6][b] * p.T[6][b] * d;
+  SERENC_TRY(run_stack(h, w.sb, p.sumT, batch, p.tmax, w.foff, attn_flops, e, st));
   return 0;
 }
 
@@ -1119,6 +1210,7 @@ extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64
   tb.hann = h->hann; tb.costab = h->costab; tb.sintab = h->sintab;
   tb.mel_ptr = h->mel_ptr; tb.mel_bin = h->mel_bin; tb.mel_w = h->mel_w; tb.n_mels = h->cfg.n_mels;
   const dim3 grid(ceil_div(LM_FRAMES, LM_FR), batch);
+  ProfScope ps(h, SERENC_PROF_LOGMEL, 3, 0.0, (double)batch * (4.0 * LM_NSAMP + 4.0 * h->cfg.n_mels * LM_FRAMES), st);
   logmel_power_kernel<<<grid, LM_THREADS, 0, st>>>(wav_dev, d_utts, tb, mel_out_dev, umax);
   SERENC_CUDA_OK(cudaGetLastError());
   const int64_t per_utt = (int64_t)h->cfg.n_mels * LM_FRAMES;
@@ -1188,19 +1280,23 @@ extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int
     SERENC_CUDA_OK(cudaMemcpyAsync(w.foff, hf, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
     SERENC_CUDA_OK(cudaMemcpyAsync(w.n_keep, hf + batch + 1, 4 * (size_t)batch, cudaMemcpyHostToDevice, st));
     SERENC_TRY(stage_commit(st));
+    ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, 0.0, st);
     whisper_plan_kernel<<<(unsigned)ceil_div64((int64_t)batch * 3002, 256), 256, 0, st>>>(batch, w.map1, w.map2);
     SERENC_CUDA_OK(cudaGetLastError());
   }
   // conv stem (HF modeling_whisper.py:619-625): gelu(conv1 k3 p1) -> gelu(conv2 k3 s2 p1) -> + positions
-  SERENC_CUDA_OK(cudaMemsetAsync(w.melrows, 0, (size_t)batch * 3002 * h->mel_pad * sizeof(bf16), st));
   {
+    ProfScope ps(h, SERENC_PROF_MISC, 3, 0.0, (double)batch * 3000 * c.n_mels * 6 + (double)batch * 3002 * d * 2, st);
+    SERENC_CUDA_OK(cudaMemsetAsync(w.melrows, 0, (size_t)batch * 3002 * h->mel_pad * sizeof(bf16), st));
+    SERENC_CUDA_OK(cudaMemsetAsync(w.c1, 0, (size_t)batch * 3002 * d * sizeof(bf16), st));
     const dim3 grid(ceil_div(LM_FRAMES, 32), ceil_div(c.n_mels, 32), batch);
     mel_to_rows_kernel<<<grid, 256, 0, st>>>(mel_dev, c.n_mels, w.melrows, h->mel_pad);
     SERENC_CUDA_OK(cudaGetLastError());
   }
-  SERENC_CUDA_OK(cudaMemsetAsync(w.c1, 0, (size_t)batch * 3002 * d * sizeof(bf16), st));
   {
     GemmCall g;
+    g.prof_cls = SERENC_PROF_GEMM_CONV;
+    g.alg_flops = 2.0 * batch * 3000.0 * d * c.n_mels * 3;
     g.A = w.melrows; g.a_cols = h->mel_pad; g.a_rows = (int64_t)batch * 3002; g.a_ld = h->mel_pad; g.a_stride = 1;
     g.a_kpt = h->mel_pad / GEMM_BK; g.taps = 3;
     g.M = (int64_t)batch * 3002; g.W = h->wc1; g.w_rows = d; g.n_per_group = d; g.groups = 1;
@@ -1209,9 +1305,14 @@ extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int
   }
   {
     const int64_t per_utt4 = (int64_t)1500 * d / 4;
-    broadcast_rows_kernel<<<dim3(128, batch), 256, 0, st>>>(h->pos_emb, per_utt4, w.sb.x);
-    SERENC_CUDA_OK(cudaGetLastError());
+    {
+      ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, (double)batch * 1500 * d * 4, st);
+      broadcast_rows_kernel<<<dim3(128, batch), 256, 0, st>>>(h->pos_emb, per_utt4, w.sb.x);
+      SERENC_CUDA_OK(cudaGetLastError());
+    }
     GemmCall g;
+    g.prof_cls = SERENC_PROF_GEMM_CONV;
+    g.alg_flops = 2.0 * batch * 1500.0 * d * d * 3;
     g.A = w.c1; g.a_cols = d; g.a_rows = (int64_t)batch * 3002; g.a_ld = d; g.a_stride = 2; g.a_kpt = d / GEMM_BK; g.taps = 3;
     g.M = (int64_t)batch * 1501; g.W = h->wc2; g.w_rows = d; g.n_per_group = d; g.groups = 1;
     g.bias = h->bc2; g.act = 1; g.resid = w.sb.x; g.out_f32 = w.sb.x; g.ld_f32 = d; g.rowmap = w.map2;
@@ -1222,7 +1323,7 @@ extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int
   e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
   e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
   e.sumT = sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = w.n_keep;
-  SERENC_TRY(run_stack(h, w.sb, sumT, batch, 1500, w.foff, e, st));
+  SERENC_TRY(run_stack(h, w.sb, sumT, batch, 1500, w.foff, 4.0 * 1500.0 * 1500.0 * d * batch, e, st));
   return 0;
 }
 
@@ -1270,12 +1371,12 @@ extern "C" int serenc_op_layernorm(serenc_handle* h, const float* x, int64_t row
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (out_f32) {
     if (gelu) SERENC_FAIL(SERENC_ERR_INVALID, "layernorm: gelu variant writes bf16 only");
-    SERENC_TRY((launch_ln_t<float, float, false>(x, cols, out_f32, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+    SERENC_TRY((launch_ln_t<float, float, false>(h, x, cols, out_f32, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
   }
   if (out_bf16) {
     bf16* o = reinterpret_cast<bf16*>(out_bf16);
-    if (gelu) SERENC_TRY((launch_ln_t<float, bf16, true>(x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
-    else SERENC_TRY((launch_ln_t<float, bf16, false>(x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+    if (gelu) SERENC_TRY((launch_ln_t<float, bf16, true>(h, x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
+    else SERENC_TRY((launch_ln_t<float, bf16, false>(h, x, cols, o, cols, gamma, beta, rows, cols, nullptr, nullptr, eps, st)));
   }
   return 0;
 }
@@ -1303,5 +1404,5 @@ extern "C" int serenc_op_attention(serenc_handle* h, const void* qkv, const int6
   p.hln = reinterpret_cast<const bf16*>(hln);
   const LayerW& l = h->L[wavlm ? layer : 0];
   p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
-  return launch_attn(h, p, wavlm != 0, tmax, batch, st);
+  return launch_attn(h, p, wavlm != 0, tmax, batch, 0.0, st);
 }

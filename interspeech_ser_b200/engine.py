@@ -102,6 +102,24 @@ class Engine:
             self._tls.ws = ws
         return ws
 
+    # ------------------------------------------------------------------ accounting
+    PROF_CLASSES = ("gemm_linear", "gemm_conv", "gemm_posconv", "attention", "layernorm", "conv0", "pool", "logmel", "misc",
+                    "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2")
+    GEMM_CLASSES = ("gemm_linear", "gemm_conv", "gemm_posconv", "gemm_qkv", "gemm_out", "gemm_fc1", "gemm_fc2")
+
+    def launch_count(self) -> int:
+        return int(self._lib.serenc_launch_count(self._h))
+
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(self._lib.serenc_set_profiling(self._h, int(enable)))
+
+    def get_profile(self) -> Dict[str, Dict[str, float]]:
+        n = len(self.PROF_CLASSES)
+        ms, fl, by = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _lib.check(self._lib.serenc_get_profile(self._h, n, ms, fl, by, cnt))
+        return {name: {"ms": ms[i], "flops": fl[i], "bytes": by[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROF_CLASSES)}
+
     # ------------------------------------------------------------------ wav2vec2 family
     def w2v_workspace_bytes(self, lens: Sequence[int]) -> int:
         out = C.c_size_t()

@@ -206,6 +206,8 @@ def cmd_model(name, lens=None, full_layers=True):
     w = random_init(cfg, 0)
     eng = Engine(cfg, w, 0)
     print(f"model[{name}] weights+engine {time.time() - t0:.1f}s", flush=True)
+    if isinstance(lens, str):
+        lens = [int(v) for v in lens.split(",")]
     lens = lens or [400, 401, 719, 720, 4001, 17777, 32000]
     waves = [synth_wave(7 + j, n) for j, n in enumerate(lens)]
     starts, off = [], 0
