@@ -1,0 +1,177 @@
+"""Command-line drivers with the reference's flags and on-disk layout.
+
+    python preprocessing/preprocess_speech.py  --ssl_type microsoft/wavlm-large --wav_dir W --save_path S [--n_layer -1] [--use_average y]
+    python preprocessing/preprocess_whisper.py --ssl_type openai/whisper-large-v3 --wav_dir W --save_path S ...
+
+Same contract as preprocessing/preprocess_speech.py:13-22,69-73 and preprocess_whisper.py of the reference: one
+`<basename>.pt` per input file holding a 2-D float32 tensor [T, D]; a failing file prints
+`Failed to process <path>: <error>` and the run continues; an unknown model aborts with the reference's message.
+What changes is the schedule: files are decoded by `--num_workers` host threads, length-bucketed into packed
+batches and (under torchrun) sharded over the GPUs of the box; tensors are saved as contiguous CPU tensors
+(identical `torch.load` result, no hidden 7.7 MB storage, no CUDA pinning of the consumer).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional
+
+import numpy as np
+
+
+def build_parser(whisper: bool) -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser()
+    # the reference's flags (preprocess_speech.py:13-22)
+    p.add_argument("--seed", type=int, default=7)
+    p.add_argument("--ssl_type", type=str, default="wavlm-large")
+    p.add_argument("--save_path", type=str, default="./")
+    p.add_argument("--wav_dir", type=str, default="./")
+    p.add_argument("--num_workers", type=int, default=4)
+    p.add_argument("--n_layer", type=int, default=-1)
+    p.add_argument("--use_average", type=str, default="n")
+    # additions
+    p.add_argument("--random_init", action="store_true", help="random weights (no checkpoint available offline)")
+    p.add_argument("--frame_budget", type=int, default=32768, help="max frames per packed batch")
+    p.add_argument("--skip_existing", action="store_true", help="resume: skip files whose .pt already exists")
+    p.add_argument("--pooled_path", type=str, default="", help="also save masked-mean pooled embeddings {names, embeddings[N, D]}")
+    if not whisper:
+        p.add_argument("--compat_layer_from_dir_count", action="store_true",
+                       help="literal preprocess_speech.py:41,67 behaviour: index hidden_states by the number of files already in --save_path")
+    else:
+        p.add_argument("--crop_cap_1500", action="store_true",
+                       help="crop to min(ceil(len/320), 1500) frames instead of the script's literal min(.., hidden_size) (preprocess_whisper.py:75)")
+    return p
+
+
+def run(argv: Optional[List[str]], whisper: bool) -> int:
+    args = build_parser(whisper).parse_args(argv)
+    import torch
+
+    from .audio_io import load_audio
+    from .configs import ARCH_WHISPER
+    from .modeling import AutoModel
+    from . import scheduler
+
+    average = args.use_average == "y"
+    print(f"Using average = {average}")
+    if not torch.cuda.is_available():
+        print("Error: no CUDA device visible; this extractor has no CPU path.")
+        return 2
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local_rank}")
+    print(f"Using device = {device}")
+
+    os.makedirs(args.save_path, exist_ok=True)
+    n_existing = len(os.listdir(args.save_path))
+    print(f"Save path = {args.save_path} created. It has {n_existing} files in it.")
+
+    wav_files = sorted(os.listdir(args.wav_dir))
+    print(f"{len(wav_files)} file are going to be processed...")
+    print(f"Checking files in {args.wav_dir}")
+    missing = [os.path.join(args.wav_dir, w) for w in wav_files if not os.path.isfile(os.path.join(args.wav_dir, w))]
+    if missing:
+        print("Missing files:")
+        for m in missing:
+            print(f" - {m}")
+        print("Something went wrong, make sure everything is correct before running again!")
+        return 1
+
+    print(f"Extracting features using {args.ssl_type}")
+    try:
+        model = AutoModel.from_pretrained(args.ssl_type, device=local_rank, random_init=args.random_init or None, seed=0)
+    except OSError:
+        print(f"Error: No pretrained model found with the name {args.ssl_type}")
+        print("Something went wrong, make sure everything is correct before running again!")
+        return 1
+    cfg = model.cfg
+    if (cfg.arch == ARCH_WHISPER) != whisper:
+        print(f"Error: {args.ssl_type} is {'not ' if whisper else ''}a Whisper model; use the other script")
+        return 1
+
+    layer = args.n_layer
+    if not whisper and getattr(args, "compat_layer_from_dir_count", False):
+        layer = n_existing  # preprocess_speech.py:41,67
+
+    def out_path(name):
+        return os.path.join(args.save_path, os.path.splitext(os.path.basename(name))[0] + ".pt")
+
+    todo = [w for w in wav_files if not (args.skip_existing and os.path.exists(out_path(w)))]
+
+    # ---- host ingest: decode with --num_workers threads ----
+    def load(name):
+        path = os.path.join(args.wav_dir, name)
+        try:
+            y, _ = load_audio(path, sr=16000)
+            if not whisper and len(y) < 400:
+                raise ValueError(f"{len(y)} samples is shorter than the encoder's 400-sample receptive field")
+            if len(y) == 0:
+                raise ValueError("empty audio")
+            return name, y
+        except Exception as e:  # noqa: BLE001  (reference: preprocess_speech.py:72-73)
+            print(f"Failed to process {path}: {e}")
+            return name, None
+
+    with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:
+        loaded = [(n, y) for n, y in ex.map(load, todo) if y is not None]
+    names = [n for n, _ in loaded]
+    waves = [y for _, y in loaded]
+    lengths = [len(y) for y in waves]
+
+    pooled_rows = {}
+    if waves:
+        batches, mine = scheduler.plan(cfg, lengths, world, rank, frame_budget=args.frame_budget)
+        writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+        futures = []
+        for bi in mine:
+            idx = batches[bi].indices
+            try:
+                if layer >= cfg.num_hidden_layers + 1 or layer < -(cfg.num_hidden_layers + 1):
+                    raise IndexError("tuple index out of range")  # what hidden_states[N] raises in the reference
+                kw = dict(layer=layer, average=average, want_frames=True, want_pooled=bool(args.pooled_path))
+                if whisper:
+                    kw["literal_crop"] = not args.crop_cap_1500
+                res = model.extract([waves[i] for i in idx], **kw)
+                frames_cpu = [f.cpu().contiguous() for f in res.frames]  # D2H; contiguous clone (no 1500-frame storage behind a view)
+                if res.pooled is not None:
+                    pc = res.pooled.cpu()
+                    for j, i in enumerate(idx):
+                        pooled_rows[names[i]] = pc[j]
+                for j, i in enumerate(idx):
+                    futures.append(writer.submit(torch.save, frames_cpu[j], out_path(names[i])))
+            except Exception as e:  # noqa: BLE001
+                for i in idx:
+                    print(f"Failed to process {os.path.join(args.wav_dir, names[i])}: {e}")
+        for f in futures:
+            f.result()
+        writer.shutdown()
+
+    if args.pooled_path:
+        rows = pooled_rows
+        if world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("gloo")
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(rows, gathered, dst=0)  # the path's only exchange: final host gather
+            if rank == 0:
+                rows = {}
+                for g in gathered:
+                    rows.update(g)
+        if rank == 0:
+            keys = sorted(rows)
+            emb = torch.stack([rows[k] for k in keys]) if keys else torch.empty(0, cfg.hidden_size)
+            torch.save({"names": keys, "embeddings": emb}, args.pooled_path)
+    print(f"Done: {len(names)} utterances on rank {rank}/{world}.")
+    return 0
+
+
+def main_speech(argv: Optional[List[str]] = None) -> int:
+    return run(argv, whisper=False)
+
+
+def main_whisper(argv: Optional[List[str]] = None) -> int:
+    return run(argv, whisper=True)

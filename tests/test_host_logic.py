@@ -1,0 +1,143 @@
+"""Host-side logic (CPU): configs, weight conversion, scheduler, audio ingest, HF-shaped output objects."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from interspeech_ser_b200 import audio_io, configs, scheduler
+from interspeech_ser_b200.engine import layer_mask_of
+from interspeech_ser_b200.modeling import ModelOutput
+from interspeech_ser_b200.weights import fold_weight_norm, from_hf_state_dict, random_init, slaney_mel_filters, whisper_sinusoids
+
+
+def test_model_constants():
+    c = configs.get_config("microsoft/wavlm-large")
+    assert (c.hidden_size, c.num_hidden_layers, c.num_attention_heads, c.intermediate_size, c.head_dim) == (1024, 24, 16, 4096, 64)
+    assert not c.conv_bias and c.family == "wavlm"
+    h = configs.get_config("facebook/hubert-xlarge-ls960-ft")
+    assert (h.hidden_size, h.num_hidden_layers, h.head_dim, h.intermediate_size) == (1280, 48, 80, 5120)
+    x = configs.get_config("wav2vec2-xls-r-2b")
+    assert (x.hidden_size, x.num_hidden_layers, x.head_dim, x.intermediate_size) == (1920, 48, 120, 7680)
+    w = configs.get_config("openai/whisper-large-v3")
+    assert (w.hidden_size, w.num_hidden_layers, w.num_attention_heads, w.num_mel_bins) == (1280, 32, 20, 128)
+    with pytest.raises(OSError):  # the reference catches OSError from from_pretrained (preprocess_speech.py:115-117)
+        configs.get_config("not/a-model")
+
+
+def test_layer_mask_semantics():
+    assert layer_mask_of([-1], 24) == (1 << 24, [24])
+    assert layer_mask_of([0, 3], 24) == (0b1001, [0, 3])
+    assert layer_mask_of([-4, -3, -2, -1], 24)[1] == [21, 22, 23, 24]
+    with pytest.raises(IndexError):
+        layer_mask_of([25], 24)   # hidden_states[25] on 25 states: the reference's swallowed IndexError (defect D1)
+
+
+def test_fold_weight_norm_matches_torch():
+    conv = torch.nn.Conv1d(32, 32, 16, padding=8, groups=4)
+    conv = torch.nn.utils.parametrizations.weight_norm(conv, name="weight", dim=2)
+    with torch.no_grad():
+        conv.parametrizations.weight.original0.mul_(1.7)
+    w = fold_weight_norm(conv.parametrizations.weight.original0, conv.parametrizations.weight.original1)
+    np.testing.assert_allclose(w, conv.weight.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_random_init_shapes_and_determinism():
+    cfg = configs.get_config("tiny/wavlm")
+    a, b = random_init(cfg, 0), random_init(cfg, 0)
+    assert sorted(a) == sorted(b) and all(np.array_equal(a[k], b[k]) for k in a)
+    assert a["conv0.weight"].shape == (512, 1, 10) and a["conv3.weight"].shape == (512, 512, 3)
+    assert a["posconv.weight"].shape == (128, 32, 16) and a["rel_attn_embed"].shape == (320, 2)
+    assert a["layer1.gru.weight"].shape == (8, 64) and "conv0.bias" not in a
+    w = random_init(configs.get_config("tiny/whisper"), 0)
+    assert "layer0.k.bias" not in w and w["embed_positions"].shape == (1500, 128) and w["mel_filters"].shape == (201, 80)
+
+
+def test_hf_state_dict_conversion_roundtrip():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    pytest.importorskip("transformers")
+    from oracle.make_golden import hf_model
+    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/whisper"):
+        cfg = configs.get_config(name)
+        w = random_init(cfg, 1)
+        back = from_hf_state_dict(cfg, hf_model(cfg, w).state_dict())
+        assert sorted(back) == sorted(w), name
+        for k in w:
+            np.testing.assert_allclose(back[k], w[k], rtol=1e-5, atol=1e-6, err_msg=f"{name}:{k}")
+
+
+def test_mel_filters_and_sinusoids():
+    fb = slaney_mel_filters(128)
+    assert fb.shape == (201, 128) and fb.min() >= 0 and (fb.max(axis=0) > 0).all()
+    nnz = (fb != 0).sum(axis=0)
+    assert nnz.min() >= 1 and nnz.max() <= 12          # sparse triangles: the kernel stores them as CSR
+    pos = whisper_sinusoids(1500, 1280)
+    assert pos.shape == (1500, 1280) and np.allclose(pos[0, :640], 0) and np.allclose(pos[0, 640:], 1)
+
+
+def test_scheduler_batches_cover_every_utterance_once():
+    cfg = configs.get_config("microsoft/wavlm-large")
+    rng = np.random.default_rng(0)
+    lens = [int(v) for v in rng.integers(32000, 320000, size=500)]
+    batches = scheduler.make_batches(cfg, lens, frame_budget=16384)
+    seen = sorted(i for b in batches for i in b.indices)
+    assert seen == list(range(500))
+    assert all(b.frames <= 16384 for b in batches)
+    for b in batches:  # length-sorted: bucketed by construction
+        ls = [lens[i] for i in b.indices]
+        assert ls == sorted(ls)
+    assign = scheduler.shard_batches(batches, 8)
+    assert sorted(j for a in assign for j in a) == list(range(len(batches)))
+    loads = [sum(batches[j].flops for j in a) for a in assign]
+    assert max(loads) <= 1.25 * (sum(loads) / 8) + max(b.flops for b in batches)
+    assert scheduler.shard_batches(batches, 8) == assign  # deterministic
+    with pytest.raises(ValueError):
+        scheduler.make_batches(cfg, [64000, 399])
+
+
+def test_flop_model_matches_survey():
+    # WavLM-large 4 s = 147.3 GFLOP, Whisper-large-v3 window = 2273.8 GFLOP
+    assert abs(scheduler.utterance_flops(configs.get_config("wavlm-large"), 64000) / 1e9 - 147.3) < 0.1
+    assert abs(scheduler.utterance_flops(configs.get_config("whisper-large-v3"), 1) / 1e9 - 2273.8) < 0.1
+
+
+def test_merge_rank_results():
+    merged = scheduler.merge_rank_results([{0: "a", 2: "c"}, {1: "b"}], 3)
+    assert merged == ["a", "b", "c"]
+    with pytest.raises(ValueError):
+        scheduler.merge_rank_results([{0: "a"}, {0: "b"}], 1)
+    with pytest.raises(ValueError):
+        scheduler.merge_rank_results([{0: "a"}], 2)
+
+
+def test_wav_roundtrip_and_resample(tmp_path):
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal(16000) * 0.1).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    audio_io.write_wav(p, x, 16000)
+    y, sr = audio_io.load_audio(p)
+    assert sr == 16000 and y.dtype == np.float32 and np.abs(y - x).max() <= 1.0 / 32768 + 1e-7
+    p8 = str(tmp_path / "b.wav")
+    t = np.arange(8000) / 8000.0
+    audio_io.write_wav(p8, 0.5 * np.sin(2 * np.pi * 440 * t), 8000)
+    z, sr = audio_io.load_audio(p8)
+    assert sr == 16000 and abs(len(z) - 16000) <= 1
+    with pytest.raises(ValueError):
+        (tmp_path / "c.wav").write_bytes(b"not a wav file at all")
+        audio_io.read_wav(str(tmp_path / "c.wav"))
+
+
+def test_model_output_access_patterns():
+    hs = (torch.zeros(1, 2, 3), torch.ones(1, 2, 3))
+    out = ModelOutput(last_hidden_state=hs[-1], extract_features=None, hidden_states=hs)
+    assert out.hidden_states is hs and out["hidden_states"] is hs      # both forms appear in preprocess_speech.py:56,67
+    assert out.last_hidden_state is hs[-1] and out[0] is hs[-1]
+    assert out.extract_features is None and "extract_features" not in out
+
+
+def test_cli_parsers_keep_reference_flags():
+    from interspeech_ser_b200.cli import build_parser
+    for whisper in (False, True):
+        a = build_parser(whisper).parse_args([])
+        assert (a.seed, a.ssl_type, a.save_path, a.wav_dir, a.num_workers, a.n_layer, a.use_average) == (7, "wavlm-large", "./", "./", 4, -1, "n")
