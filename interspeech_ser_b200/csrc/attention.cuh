@@ -63,12 +63,105 @@ __device__ __forceinline__ void att_load_tile(uint8_t* smem_tile, const bf16* gb
   }
 }
 
+// One 16-query x 64-key tile step of one warp: S = Q K^T, scale + gated bias + mask, online softmax, O += P V.
+// FULL = all 64 keys valid (no mask, no group skipping; keeps the instruction stream branch-free so the MMAs and
+// exp2s of different 8-key groups interleave); !FULL = the utterance's last, ragged key tile.
+template <int HD, bool WAVLM, bool FULL>
+__device__ __forceinline__ void att_tile_step(const uint8_t* kt_s, const uint8_t* vt_s, const uint32_t (&qf)[AttnCfg<HD>::KSTEPS][4],
+                                              float (&o_acc)[2 * AttnCfg<HD>::NP_O][4], float (&m_run)[2], float (&l_run)[2],
+                                              const float (&gate_r)[2], const float* bwin, float sc2, int nvalid, int warp,
+                                              int lane) {
+  using C = AttnCfg<HD>;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int npairs = FULL ? 4 : ((nvalid + 15) >> 4);
+  float s[8][4];
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    s[2 * np][0] = s[2 * np][1] = s[2 * np][2] = s[2 * np][3] = 0.f;
+    s[2 * np + 1][0] = s[2 * np + 1][1] = s[2 * np + 1][2] = s[2 * np + 1][3] = 0.f;
+    if (FULL || np < npairs) {
+#pragma unroll
+      for (int ks = 0; ks < C::KSTEPS; ++ks) {
+        const int mi = lane >> 3;
+        const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
+        const int chunk = 2 * ks + (mi & 1);
+        uint32_t kb[4];
+        ldmatrix_x4(kb, smem_u32(kt_s + key * (C::DP * 2) + ((chunk ^ (key & 7)) << 4)));
+        mma_bf16_16816(s[2 * np], qf[ks], kb[0], kb[1]);
+        mma_bf16_16816(s[2 * np + 1], qf[ks], kb[2], kb[3]);
+      }
+    }
+  }
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (FULL || (nt >> 1) < npairs) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + 2 * t4 + (e & 1);
+        float v = s[nt][e] * sc2;
+        if (WAVLM) v = fmaf(gate_r[e >> 1], bwin[col - (warp * 16 + g + (e >> 1) * 8) + 63], v);
+        if (!FULL && col >= nvalid) v = -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+  }
+  float alpha[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every key tile holds at least one valid key
+    alpha[r] = exp2f(m_run[r] - m_new);
+    m_run[r] = m_new;
+    l_run[r] *= alpha[r];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (FULL || (nt >> 1) < npairs) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[nt][e] - m_run[e >> 1]);
+        s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2 * C::NP_O; ++i) {
+    o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
+    o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+  }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    if (FULL || kk < npairs) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < C::NP_O; ++dp) {
+        const int mi = lane >> 3;
+        const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+        const int chunk = 2 * dp + (mi >> 1);
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, smem_u32(vt_s + key * (C::DP * 2) + ((chunk ^ (key & 7)) << 4)));
+        mma_bf16_16816(o_acc[2 * dp], pa, vb[0], vb[1]);
+        mma_bf16_16816(o_acc[2 * dp + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+}
+
 template <int HD, bool WAVLM>
-__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, (HD == 64) ? 4 : 2) attention_fwd_kernel(const AttnParams p) {
   using C = AttnCfg<HD>;
   extern __shared__ __align__(128) uint8_t att_smem[];
   __shared__ float s_bwin[2][128];
   __shared__ float s_gate[ATT_BM];
+  __shared__ float4 s_gw[WAVLM ? HD * 2 : 1];  // gru_rel_pos_linear weight, [k][8 outputs] as two float4
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = p.frame_off[b];
@@ -92,21 +185,33 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttnPa
   cp_async_commit();
 
   if (WAVLM) {
-    // gate for the 64 query rows: two threads per row, each half of the head dims
+    // gate for the 64 query rows (HF modeling_wavlm.py:167-176): two threads per row, each half of the head dims;
+    // the 8 x HD weight is staged transposed in shared memory so every k costs two broadcast float4 reads.
+    float* gw = reinterpret_cast<float*>(s_gw);
+    for (int i = tid; i < 8 * HD; i += ATT_THREADS) {
+      const int o = i / HD, k = i - o * HD;
+      gw[k * 8 + o] = __ldg(p.gru_w + i);
+    }
+    __syncthreads();
     const int row = tid >> 1, half = tid & 1;
     float acc[8];
 #pragma unroll
     for (int o = 0; o < 8; ++o) acc[o] = 0.f;
     if (i0 + row < T) {
       const bf16* x = p.hln + (int64_t)(r0 + i0 + row) * p.d + h * HD + half * (HD / 2);
+#pragma unroll 4
       for (int k = 0; k < HD / 2; k += 2) {
         const float2 xv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + k));
-#pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          const float* w = p.gru_w + o * HD + half * (HD / 2) + k;
-          acc[o] = fmaf(xv.x, __ldg(w), acc[o]);
-          acc[o] = fmaf(xv.y, __ldg(w + 1), acc[o]);
-        }
+        const int kk = half * (HD / 2) + k;
+        const float4 w0 = s_gw[kk * 2], w1 = s_gw[kk * 2 + 1], w2 = s_gw[kk * 2 + 2], w3 = s_gw[kk * 2 + 3];
+        acc[0] = fmaf(xv.x, w0.x, acc[0]); acc[1] = fmaf(xv.x, w0.y, acc[1]);
+        acc[2] = fmaf(xv.x, w0.z, acc[2]); acc[3] = fmaf(xv.x, w0.w, acc[3]);
+        acc[4] = fmaf(xv.x, w1.x, acc[4]); acc[5] = fmaf(xv.x, w1.y, acc[5]);
+        acc[6] = fmaf(xv.x, w1.z, acc[6]); acc[7] = fmaf(xv.x, w1.w, acc[7]);
+        acc[0] = fmaf(xv.y, w2.x, acc[0]); acc[1] = fmaf(xv.y, w2.y, acc[1]);
+        acc[2] = fmaf(xv.y, w2.z, acc[2]); acc[3] = fmaf(xv.y, w2.w, acc[3]);
+        acc[4] = fmaf(xv.y, w3.x, acc[4]); acc[5] = fmaf(xv.y, w3.y, acc[5]);
+        acc[6] = fmaf(xv.y, w3.z, acc[6]); acc[7] = fmaf(xv.y, w3.w, acc[7]);
       }
     }
 #pragma unroll
@@ -135,6 +240,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttnPa
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
   float gate_r[2] = {0.f, 0.f};
+  // Tile quantisation: a warp whose 16 query rows are all past the utterance end does no math (it still helps
+  // with the cooperative loads), and 16-key groups past the last valid key are skipped in the ragged last tile:
+  // T = 199 pays for 208 x 208, not 256 x 256.
+  const bool warp_active = (i0 + warp * 16) < T;
 
   for (int kt = 0; kt < nkt; ++kt) {
     const int buf = kt & 1;
@@ -167,90 +276,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const AttnPa
         gate_r[1] = s_gate[warp * 16 + g + 8];
       }
     }
-
-    // ---- S = Q K^T (16 x 64 per warp) ----
-    float s[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    const uint8_t* kt_s = sK + buf * C::TILE_BYTES;
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-#pragma unroll
-      for (int ks = 0; ks < C::KSTEPS; ++ks) {
-        const int mi = lane >> 3;
-        const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
-        const int chunk = 2 * ks + (mi & 1);
-        uint32_t kb[4];
-        ldmatrix_x4(kb, smem_u32(kt_s + key * (C::DP * 2) + ((chunk ^ (key & 7)) << 4)));
-        mma_bf16_16816(s[2 * np], qf[ks], kb[0], kb[1]);
-        mma_bf16_16816(s[2 * np + 1], qf[ks], kb[2], kb[3]);
-      }
-    }
-
-    // ---- scale, bias, mask, online softmax (log2 domain) ----
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + 2 * t4 + (e & 1);
-        const int rl = warp * 16 + g + (e >> 1) * 8;
-        float v = s[nt][e] * sc2;
-        if (WAVLM) v = fmaf(gate_r[e >> 1], s_bwin[buf][col - rl + 63], v);
-        if (j0 + col >= T) v = -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
-      }
-    }
-    float alpha[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every key tile holds at least one valid key
-      alpha[r] = exp2f(m_run[r] - m_new);
-      m_run[r] = m_new;
-      l_run[r] *= alpha[r];
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f(s[nt][e] - m_run[e >> 1]);
-        s[nt][e] = pv;
-        l_run[e >> 1] += pv;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 2 * C::NP_O; ++i) {
-      o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
-      o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
-    }
-
-    // ---- O += P V ----
-    const uint8_t* vt_s = sV + buf * C::TILE_BYTES;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int dp = 0; dp < C::NP_O; ++dp) {
-        const int mi = lane >> 3;
-        const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
-        const int chunk = 2 * dp + (mi >> 1);
-        uint32_t vb[4];
-        ldmatrix_x4_trans(vb, smem_u32(vt_s + key * (C::DP * 2) + ((chunk ^ (key & 7)) << 4)));
-        mma_bf16_16816(o_acc[2 * dp], pa, vb[0], vb[1]);
-        mma_bf16_16816(o_acc[2 * dp + 1], pa, vb[2], vb[3]);
-      }
+    if (warp_active) {
+      const uint8_t* kt_s = sK + buf * C::TILE_BYTES;
+      const uint8_t* vt_s = sV + buf * C::TILE_BYTES;
+      if (j0 + ATT_BN <= T)
+        att_tile_step<HD, WAVLM, true>(kt_s, vt_s, qf, o_acc, m_run, l_run, gate_r, s_bwin[buf], sc2, ATT_BN, warp, lane);
+      else
+        att_tile_step<HD, WAVLM, false>(kt_s, vt_s, qf, o_acc, m_run, l_run, gate_r, s_bwin[buf], sc2, T - j0, warp, lane);
     }
     __syncthreads();
   }
 
   // ---- finalize ----
+  if (!warp_active) return;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);

@@ -1,9 +1,17 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M, N] = epilogue(A[M, K] * W[N, K]^T)
+// Persistent, warp-specialised bf16 GEMMs for sm_100a:  D[M, N] = epilogue(A[M, K] * W[N, K]^T)
 //
-//   TMA (cp.async.bulk.tensor, 128B swizzle) -> 4..8-stage shared-memory ring -> tcgen05.mma (one issuing
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> multi-stage shared-memory ring -> tcgen05.mma (one issuing
 //   thread, fp32 accumulators in TMEM, double-buffered so the epilogue of tile i overlaps the mainloop of
 //   tile i+1) -> tcgen05.ld epilogue with fused bias / exact GELU / fp32 residual add / bf16 down-cast and an
 //   optional output row map.
+//
+// Two kernels share the operand addressing and the epilogue:
+//   * gemm_bf16_tcgen05_2cta_kernel — the workhorse. A CTA pair (cluster of 2 = one TPC) computes a 256 x 256
+//     tile with tcgen05.mma.cta_group::2: each CTA stages only its 128 rows of A and its 128 rows of W per
+//     K-block (32 KB instead of the 48 KB a 128 x 256 single-CTA tile needs), which is what lifts the kernel off
+//     the L2->SM bandwidth ceiling measured with the single-CTA version (profiles/r01_notes.md).
+//   * gemm_bf16_tcgen05_kernel<BN> (BN = 64 | 128) — single-CTA 128 x BN tiles for narrow outputs (the grouped
+//     positional conv has 64..120 columns per group) and for problems too small to fill 74 CTA pairs.
 //
 // Every Linear / Conv1d on the embedding-extraction path is an implicit GEMM over channels-last activations;
 // no im2col buffer exists. The K loop is decomposed into (tap, 64-channel block):
@@ -16,8 +24,11 @@
 //   * grouped positional Conv1d (k=128, groups=16; modeling_wavlm.py:48-90): s = 1, 128 taps, the group picks
 //     the column block. W is packed [N, tap*C_pad + c] to match.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4) .. +31, one accumulator row per thread).
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..11 = epilogue. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per thread, the only
+// shape tcgen05.ld offers) for its half of the tile's columns, transposes each 32x32 block through a padded
+// shared-memory tile and then touches global memory with lanes running along a row: bias / GELU / residual /
+// stores are all 128-byte-coalesced (the row-per-thread layout would cost 32 sectors per request).
 #pragma once
 #include "common.cuh"
 
@@ -25,7 +36,12 @@ namespace serenc {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_ST_LD = 36;  // staging row stride in words: 16-byte aligned rows, conflict-free 128-bit accesses
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * GEMM_ST_LD * 4;  // per-warp padded 32x32 fp32 transpose tile
+constexpr int GEMM2_BN = 256;     // 2-CTA kernel: tile is 256 (M, 128 per CTA) x 256 (N, W rows split 128 per CTA)
+constexpr int GEMM2_STAGES = 5;
 
 struct GemmParams {
   int64_t M;         // rows of A (tensor-map extent)
@@ -49,15 +65,109 @@ struct GemmParams {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 128) ? 5 : 6;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256 / 512: power of two
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // 128 / 256: power of two
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
 };
 
+struct Gemm2Cfg {
+  static constexpr int STAGES = GEMM2_STAGES;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (GEMM2_BN / 2) * GEMM_BK * 2; // this CTA's 128 rows of W
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KB
+  static constexpr int TMEM_COLS = 512;                        // 2 x 256 accumulator columns
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces
+// ------------------------------------------------------------------------------------------------
+struct TileCoord {
+  int m_t, g, n_t;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  const int tiles_per_m = p.tiles_n * p.groups;
+  TileCoord t;
+  t.m_t = tile / tiles_per_m;
+  const int rem = tile - t.m_t * tiles_per_m;
+  t.g = rem / p.tiles_n;
+  t.n_t = rem - t.g * p.tiles_n;
+  return t;
+}
+
+// Epilogue of one warp for its 32 rows x NCOLS columns of an accumulator.
+//   t_addr : TMEM address of (lane quarter, first column)   row0 : first of the warp's 32 rows
+//   n0     : first column (within the group) of the warp's column range
+template <int NCOLS>
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* st, uint32_t t_addr, int64_t row0, int g,
+                                                   int n0, int lane) {
+  const int sr = lane >> 3;       // coalesced phase: sub-row 0..3
+  const int c4 = (lane & 7) * 4;  // coalesced phase: 4 consecutive columns
+  int64_t orow[8];                // output rows this lane touches in the coalesced phase
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + 4 * i + sr;
+    orow[i] = -1;
+    if (r < p.M) orow[i] = p.rowmap ? (int64_t)__ldg(p.rowmap + r) : r;
+  }
+#pragma unroll 1
+  for (int c = 0; c < NCOLS / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= p.n_per_group) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<uint4*>(st + lane * GEMM_ST_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    __syncwarp();
+    const int col = col0 + c4;
+    if (col < p.n_per_group) {
+      const int gcol = g * p.n_per_group + col;
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+      // residual loads first, all 8 in flight (in-place update: a load behind a possibly aliasing store
+      // would serialise on the ~1 us DRAM latency)
+      float4 q[8];
+      if (p.resid) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (orow[i] >= 0) q[i] = *reinterpret_cast<const float4*>(p.resid + orow[i] * p.ld_f32 + gcol);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (orow[i] < 0) continue;
+        float4 v = *reinterpret_cast<const float4*>(st + (4 * i + sr) * GEMM_ST_LD + c4);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        if (p.act == 1) {
+          v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+        }
+        if (p.resid) {
+          v.x += q[i].x; v.y += q[i].y; v.z += q[i].z; v.w += q[i].w;
+        }
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[i] * p.ld_f32 + gcol) = v;
+        if (p.out_bf16) {
+          uint2 u;
+          u.x = pack_bf16x2(v.x, v.y);
+          u.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(p.out_bf16 + orow[i] * p.ld_bf16 + gcol) = u;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-CTA kernel: 128 x BN tiles
+// ------------------------------------------------------------------------------------------------
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -68,7 +178,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + GEMM_STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
@@ -89,7 +200,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);  // every epilogue thread arrives
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);  // lane 0 of every epilogue warp arrives
     }
     fence_mbar_init();
   }
@@ -102,8 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_m = p.tiles_n * p.groups;
-  const int num_tiles = p.tiles_m * tiles_per_m;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.groups;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -111,18 +221,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_t = tile / tiles_per_m;
-        const int rem = tile - m_t * tiles_per_m;
-        const int g = rem / p.tiles_n;
-        const int n_t = rem - g * p.tiles_n;
-        const int m0 = m_t * GEMM_BM;
-        const int wrow0 = g * p.n_per_group + n_t * BN;
+        const TileCoord tc = decode_tile(p, tile);
+        const int m0 = tc.m_t * GEMM_BM;
+        const int wrow0 = tc.g * p.n_per_group + tc.n_t * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int tap = kb / p.a_kpt;
           const int cc = kb - tap * p.a_kpt;
-          const int acol = g * p.a_group_stride + cc * GEMM_BK;
+          const int acol = tc.g * p.a_group_stride + cc * GEMM_BK;
           if (p.a_stride == 2) {
             tma_load_2d(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, &full_bar[stage], acol, m0 + (tap >> 1));
           } else {
@@ -172,86 +279,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp & 3;
+    const int ew = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;        // which half of the tile's columns
+    float* st = staging + (warp - 4) * (32 * GEMM_ST_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_t = tile / tiles_per_m;
-      const int rem = tile - m_t * tiles_per_m;
-      const int g = rem / p.tiles_n;
-      const int n_t = rem - g * p.tiles_n;
-      const int64_t row = (int64_t)m_t * GEMM_BM + ew * 32 + lane;
-      const int n0 = n_t * BN;
-
-      int64_t orow = -1;
-      if (row < p.M) orow = p.rowmap ? (int64_t)p.rowmap[row] : row;
-      const bool row_ok = orow >= 0;
-
+      const TileCoord tc = decode_tile(p, tile);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
-        const int col0 = n0 + c * 16;
-        if (col0 >= p.n_per_group) break;  // warp-uniform
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int gcol = g * p.n_per_group + col0;
-          const int nvalid = min(16, p.n_per_group - col0);  // 8 or 16
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (j < nvalid) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (p.resid) {
-            const float* rp = p.resid + orow * p.ld_f32 + gcol;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (j < nvalid) {
-                const float4 q = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float* op = p.out_f32 + orow * p.ld_f32 + gcol;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              if (j < nvalid) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-          }
-          if (p.out_bf16) {
-            bf16* op = p.out_bf16 + orow * p.ld_bf16 + gcol;
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              if (j < nvalid) {
-                uint4 u;
-                u.x = pack_bf16x2(v[j], v[j + 1]);
-                u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(op + j) = u;
-              }
-            }
-          }
-        }
-      }
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      gemm_epilogue_warp<BN / 2>(p, st, t_addr, (int64_t)tc.m_t * GEMM_BM + ew * 32, tc.g, tc.n_t * BN + half * (BN / 2), lane);
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -263,6 +304,152 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair kernel: 256 x 256 tiles, tcgen05.mma.cta_group::2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                              const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = GEMM2_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + GEMM_STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's producer arrives (expect_tx covers both CTAs' TMA bytes)
+      mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);                    // multicast tcgen05.commit from the leader
+      mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);  // every epilogue warp of both CTAs (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // peer barriers initialised + both allocations done before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n * p.groups;   // tiles_m counts 256-row tiles here
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int m0 = tc.m_t * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+        const int wrow0 = tc.g * p.n_per_group + tc.n_t * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t leader_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const int tap = kb / p.a_kpt;
+          const int cc = kb - tap * p.a_kpt;
+          const int acol = tc.g * p.a_group_stride + cc * GEMM_BK;
+          if (p.a_stride == 2) {
+            tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, leader_bar, acol, m0 + (tap >> 1));
+          } else {
+            tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &tmA0, leader_bar, acol, m0 + tap);
+          }
+          tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, &tmB, leader_bar, kb * GEMM_BK, wrow0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_bf16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((kb | k) != 0));
+          }
+          umma_commit_2cta(&empty_bar[stage]);  // frees this smem slot in BOTH CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2cta(&tfull_bar[acc]);  // accumulator complete, signalled to both CTAs' epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float* st = staging + (warp - 4) * (32 * GEMM_ST_LD);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileCoord tc = decode_tile(p, tile);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      const int64_t row0 = (int64_t)tc.m_t * (2 * GEMM_BM) + (int64_t)rank * GEMM_BM + ew * 32;
+      gemm_epilogue_warp<BN / 2>(p, st, t_addr, row0, tc.g, tc.n_t * BN + half * (BN / 2), lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();   // no CTA of the pair may exit while the other can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

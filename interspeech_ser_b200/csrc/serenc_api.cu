@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <array>
@@ -102,6 +103,7 @@ struct serenc_handle {
   // launch accounting / optional per-class device timing (bench.py's roofline numbers)
   std::atomic<long long> launches{0};
   bool prof = false;
+  bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
 };
@@ -286,12 +288,70 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   if (tiles <= 0) return 0;
   const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
   const double flops = c.alg_flops >= 0 ? c.alg_flops : 2.0 * (double)c.M * c.n_per_group * c.groups * p.num_kb * GEMM_BK;
-  const double bytes = 2.0 * ((double)c.M * p.num_kb * GEMM_BK / (c.taps > 1 ? c.taps : 1) * c.groups / (c.groups > 1 ? c.groups : 1) +
-                              (double)c.w_rows * p.num_kb * GEMM_BK) +
+  const double bytes = 2.0 * ((double)c.M * c.a_cols / (c.groups > 1 ? 1 : 1) + (double)c.w_rows * p.num_kb * GEMM_BK) +
                        (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
   ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
   SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// CTA-pair kernel: 256 x 256 tiles, launched as clusters of 2
+int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
+  using Cfg = Gemm2Cfg;
+  GemmParams p;
+  p.M = c.M;
+  p.n_per_group = c.n_per_group;
+  p.groups = c.groups;
+  p.num_kb = c.taps * c.a_kpt;
+  p.tiles_m = (int)ceil_div64(c.M, 2 * GEMM_BM);
+  p.tiles_n = ceil_div(c.n_per_group, GEMM2_BN);
+  p.a_kpt = c.a_kpt;
+  p.a_stride = c.a_stride;
+  p.a_group_stride = c.a_group_stride;
+  p.bias = c.bias;
+  p.resid = c.resid;
+  p.out_f32 = c.out_f32;
+  p.ld_f32 = c.ld_f32;
+  p.out_bf16 = c.out_bf16;
+  p.ld_bf16 = c.ld_bf16;
+  p.rowmap = c.rowmap;
+  p.act = c.act;
+
+  CUtensorMap tA0, tA1, tB;
+  const uint64_t s = (uint64_t)c.a_stride;
+  SERENC_TRY(get_tmap(h, c.A, (uint64_t)c.a_cols, (uint64_t)ceil_div64(c.a_rows, (int64_t)s), (uint64_t)c.a_ld * s * 2,
+                      GEMM_BM, &tA0));
+  if (c.a_stride == 2) {
+    SERENC_TRY(get_tmap(h, c.A + c.a_ld, (uint64_t)c.a_cols, (uint64_t)(c.a_rows / 2 > 0 ? c.a_rows / 2 : 1),
+                        (uint64_t)c.a_ld * 4, GEMM_BM, &tA1));
+  } else {
+    tA1 = tA0;
+  }
+  const uint64_t wk = c.w_k > 0 ? (uint64_t)c.w_k : (uint64_t)p.num_kb * GEMM_BK;
+  SERENC_TRY(get_tmap(h, c.W, wk, (uint64_t)c.w_rows, wk * 2, GEMM2_BN / 2, &tB));
+
+  const int64_t tiles = (int64_t)p.tiles_m * p.tiles_n * p.groups;
+  if (tiles <= 0) return 0;
+  const int max_pairs = h->num_sms / 2;
+  const int pairs = (int)(tiles < max_pairs ? tiles : max_pairs);
+  const double flops = c.alg_flops >= 0 ? c.alg_flops : 2.0 * (double)c.M * c.n_per_group * c.groups * p.num_kb * GEMM_BK;
+  const double bytes = 2.0 * ((double)c.M * c.a_cols + (double)c.w_rows * p.num_kb * GEMM_BK) +
+                       (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
+  ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel, tA0, tA1, tB, p));
   return 0;
 }
 
@@ -300,9 +360,9 @@ int launch_gemm(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   if ((c.a_ld % 8) != 0 || (c.a_group_stride % 8) != 0 || (c.w_k % 8) != 0)
     SERENC_FAIL(SERENC_ERR_INVALID, "gemm: A leading dimension must be a multiple of 8 elements");
   if (c.n_per_group <= 64) return launch_gemm_bn<64>(h, c, st);
-  if (c.n_per_group <= 128) return launch_gemm_bn<128>(h, c, st);
-  const int64_t tiles256 = ceil_div64(c.M, GEMM_BM) * ceil_div(c.n_per_group, 256) * c.groups;
-  if (tiles256 >= h->num_sms) return launch_gemm_bn<256>(h, c, st);
+  // wide outputs with enough work for the CTA pairs: 256 x 256 tiles on tcgen05.mma.cta_group::2
+  const int64_t tiles2 = ceil_div64(c.M, 2 * GEMM_BM) * ceil_div(c.n_per_group, GEMM2_BN) * c.groups;
+  if (c.n_per_group >= 192 && tiles2 >= h->num_sms / 4 && !h->force_1cta) return launch_gemm_2cta(h, c, st);
   return launch_gemm_bn<128>(h, c, st);
 }
 
@@ -551,6 +611,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->head_dim = hd;
+  { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
   *out = h;
 
   int st = 0;
@@ -598,7 +659,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     auto attr = [&](cudaError_t e) { if (e != cudaSuccess && !st) { st = SERENC_ERR_CUDA; serenc::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); } };
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
   }
   if (st) {
