@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libserenc.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libserenc.stamp")
 
 SOURCES = ["serenc_api.cu"]
-HEADERS = ["common.cuh", "gemm_tcgen05.cuh", "attention.cuh", "frontend_norm.cuh", "logmel.cuh"]
+HEADERS = ["common.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tc.cuh", "frontend_norm.cuh", "logmel.cuh"]
 
 
 def _nvcc() -> str:

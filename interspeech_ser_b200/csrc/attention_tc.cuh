@@ -1,0 +1,358 @@
+// tcgen05 flash attention for head_dim 64 (WavLM-large, wav2vec2/HuBERT-large, Whisper): packed variable-length,
+// non-causal, optional WavLM gated relative-position bias.
+//
+// One CTA = 128 query rows of one (utterance, head). Both GEMMs of the attention run on the 5th-gen tensor cores
+// with accumulators in TMEM; the softmax runs one query row per thread straight out of TMEM, so there are no
+// cross-lane reductions and none of the ldmatrix / mma.sync fragment traffic of the previous kernel:
+//
+//   control thread (warp 4):  TMA Q, K_j, V_j  ->  S = Q K_j^T (tcgen05.mma, N = 128)  ->  ...  ->  O += P_j V_j
+//   softmax threads (warps 0-3, thread r <-> query row r <-> TMEM lane r):
+//        tcgen05.ld S row -> scale (+ gate * bias[key - query]) -> running max / sum (exp2 domain)
+//        -> rescale O in TMEM when the max moved (tcgen05.ld / tcgen05.st) -> P (bf16) into shared memory in the
+//        128B-swizzled K-major layout the second MMA reads -> final O / l -> bf16 rows of the output.
+//
+// Keys are processed 64 at a time. TMEM: S = columns [0, 64), O = columns [64, 128) of a 128-column allocation;
+// shared memory Q 16 KB + K 8 KB + V 8 KB + P 16 KB, single-buffered (K_{j+1} is fetched as soon as S_j is
+// complete, V_{j+1} as soon as O += P_j V_j is). The phases of one CTA are serial; FOUR CTAs per SM (<= 80
+// registers: the softmax makes two passes over S in TMEM instead of holding the row) overlap one CTA's softmax
+// with the others' MMAs and loads.
+// V is consumed as an MN-major (head-dim contiguous) B operand directly from its row-major [key, d] tile.
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+
+namespace serenc {
+
+constexpr int FA_BM = 128;   // query rows per CTA (= TMEM lanes)
+constexpr int FA_BN = 64;    // keys per block
+constexpr int FA_HD = 64;
+constexpr int FA_THREADS = 160;
+constexpr int FA_Q_BYTES = FA_BM * FA_HD * 2;   // 16 KB
+constexpr int FA_KV_BYTES = FA_BN * FA_HD * 2;  // 8 KB
+constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;   // 16 KB
+constexpr int FA_WIN = FA_BM + FA_BN - 1;       // bias window entries per (q tile, key block)
+constexpr int FA_SMEM_BYTES = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + 8 * FA_HD * 4 /*gate weights*/ +
+                              2 * 192 * 4 /*bias windows*/ + 64 /*barriers*/ + 1024;
+constexpr int FA_TMEM_COLS = 128;
+constexpr int FA_TMEM_S = 0, FA_TMEM_O = 64;
+
+// MN-major (N contiguous), 128B-swizzled B operand: 8-row (K) groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_group_sync() {  // the 128 softmax threads only (named barrier 1)
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+template <bool WAVLM>
+__global__ void __launch_bounds__(FA_THREADS, 4)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  extern __shared__ uint8_t fa_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + FA_Q_BYTES;
+  uint8_t* sV = sK + FA_KV_BYTES;
+  uint8_t* sP = sV + FA_KV_BYTES;
+  float4* s_gw = reinterpret_cast<float4*>(sP + FA_P_BYTES);  // [k][8 outputs]
+  float* s_win = reinterpret_cast<float*>(sP + FA_P_BYTES + 8 * FA_HD * 4);  // [2][192]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES + 8 * FA_HD * 4 + 2 * 192 * 4);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p = bars + 4;
+  uint64_t* bar_o = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = p.frame_off[b];
+  const int T = p.frame_off[b + 1] - r0;
+  const int i0 = blockIdx.x * FA_BM;
+  if (i0 >= T) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkv = (T + FA_BN - 1) / FA_BN;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      mbar_init(bar_q, 1);
+      mbar_init(bar_k, 1);
+      mbar_init(bar_v, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_p, 128);
+      mbar_init(bar_o, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (WAVLM) {
+    float* gw = reinterpret_cast<float*>(s_gw);
+    for (int i = tid; i < 8 * FA_HD; i += FA_THREADS) {
+      const int o = i / FA_HD, k = i - o * FA_HD;
+      gw[k * 8 + o] = __ldg(p.gru_w + i);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------ control: TMA + MMA issue ------------------------------
+    if (lane == 0) {
+      const int colq = h * FA_HD, colk = p.d + h * FA_HD, colv = 2 * p.d + h * FA_HD;
+      mbar_arrive_expect_tx(bar_q, FA_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, colq, r0 + i0);
+      mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
+      tma_load_2d(sK, &tmKV, bar_k, colk, r0);
+      mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
+      tma_load_2d(sV, &tmKV, bar_v, colv, r0);
+      constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);                 // Q K^T: both K-major
+      constexpr uint32_t idesc_o = umma_idesc_bf16(FA_BM, FA_HD) | (1u << 16);    // P V: B (= V) MN-major
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const uint32_t ph = (uint32_t)(j & 1);
+        mbar_wait(bar_k, ph);
+        tc_fence_after();
+        {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sQ));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+          for (int k = 0; k < FA_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + FA_TMEM_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+          umma_commit(bar_s);
+        }
+        mbar_wait(bar_s, ph);  // S complete => K tile free
+        if (j + 1 < nkv) {
+          mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
+          tma_load_2d(sK, &tmKV, bar_k, colk, r0 + (j + 1) * FA_BN);
+        }
+        mbar_wait(bar_p, ph);  // P_j in shared memory, O rescaled
+        tc_fence_after();
+        mbar_wait(bar_v, ph);
+        tc_fence_after();
+        {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sP));
+#pragma unroll
+          for (int k = 0; k < FA_BN / 16; ++k) {
+            // A = P: +32 B per 16 keys inside the swizzle row; B = V (MN-major): 16 keys = 16 rows of 128 B
+            const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + k * 16 * 128));
+            umma_bf16_ss(tmem_base + FA_TMEM_O, adesc + (uint64_t)(2 * k), bdesc, idesc_o, (uint32_t)((j | k) != 0));
+          }
+          umma_commit(bar_o);
+        }
+        mbar_wait(bar_o, ph);  // O += P V complete => V tile and P free
+        if (j + 1 < nkv) {
+          mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
+          tma_load_2d(sV, &tmKV, bar_v, colv, r0 + (j + 1) * FA_BN);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ softmax: one query row per thread ------------------------------
+    const int row = tid;                       // 0..127 == TMEM lane
+    const int qi = i0 + row;                   // query index inside the utterance
+    const bool row_valid = qi < T;
+    const bool warp_valid = (i0 + warp * 32) < T;  // warp-uniform
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float sc2 = p.scale * LOG2E;
+
+    float gate = 0.f;
+    if (WAVLM && row_valid) {
+      // gate (HF modeling_wavlm.py:167-176) from the layer input row of this head
+      const uint4* x4 = reinterpret_cast<const uint4*>(p.hln + (int64_t)(r0 + qi) * p.d + h * FA_HD);
+      float acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll 2
+      for (int c = 0; c < FA_HD / 8; ++c) {
+        const uint4 u = __ldg(x4 + c);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xv = unpack_bf16x2(uu[e]);
+          const int k = c * 8 + e * 2;
+          const float4 w0 = s_gw[k * 2], w1 = s_gw[k * 2 + 1], w2 = s_gw[k * 2 + 2], w3 = s_gw[k * 2 + 3];
+          acc[0] = fmaf(xv.x, w0.x, acc[0]); acc[1] = fmaf(xv.x, w0.y, acc[1]);
+          acc[2] = fmaf(xv.x, w0.z, acc[2]); acc[3] = fmaf(xv.x, w0.w, acc[3]);
+          acc[4] = fmaf(xv.x, w1.x, acc[4]); acc[5] = fmaf(xv.x, w1.y, acc[5]);
+          acc[6] = fmaf(xv.x, w1.z, acc[6]); acc[7] = fmaf(xv.x, w1.w, acc[7]);
+          acc[0] = fmaf(xv.y, w2.x, acc[0]); acc[1] = fmaf(xv.y, w2.y, acc[1]);
+          acc[2] = fmaf(xv.y, w2.z, acc[2]); acc[3] = fmaf(xv.y, w2.w, acc[3]);
+          acc[4] = fmaf(xv.y, w3.x, acc[4]); acc[5] = fmaf(xv.y, w3.y, acc[5]);
+          acc[6] = fmaf(xv.y, w3.z, acc[6]); acc[7] = fmaf(xv.y, w3.w, acc[7]);
+        }
+      }
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        sa += acc[o] + __ldg(p.gru_b + o);
+        sb += acc[o + 4] + __ldg(p.gru_b + o + 4);
+      }
+      const float ga = 1.f / (1.f + __expf(-sa));
+      const float gb = 1.f / (1.f + __expf(-sb));
+      gate = (ga * (gb * __ldg(p.gru_const + h) - 1.f) + 2.f) * LOG2E;
+    }
+    const float* btab_h = WAVLM ? p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1) : nullptr;
+
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      const int j0 = j * FA_BN;
+      const int ncols = min(FA_BN, T - j0);
+      // bias window of this (query tile, key block): win[x] = bias_h[j0 - i0 - 127 + x], x = col - row + 127
+      const float* win = s_win + (j & 1) * 192 + (FA_BM - 1 - row);   // win[col] == bias_h[(j0 + col) - qi]
+      if (WAVLM) {
+        float* wbuf = s_win + (j & 1) * 192;
+        for (int x = tid; x < FA_WIN; x += 128) {
+          int dlt = j0 - i0 - (FA_BM - 1) + x;
+          dlt = max(-(WAVLM_MAXD - 1), min(WAVLM_MAXD - 1, dlt));   // buckets saturate at |delta| >= 778
+          wbuf[x] = __ldg(btab_h + dlt);
+        }
+        softmax_group_sync();
+      }
+      mbar_wait(bar_s, ph);
+      tc_fence_after();
+
+      // pass 1: row maximum of  s * scale * log2e + gate * bias
+      float mx = -INFINITY;
+      if (warp_valid) {
+#pragma unroll
+        for (int c = 0; c < FA_BN / 32; ++c) {
+          if (c * 32 < ncols) {  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int col = c * 32 + k;
+              float x = __uint_as_float(r[k]) * sc2;
+              if (WAVLM) x = fmaf(gate, win[col], x);
+              if (col < ncols) mx = fmaxf(mx, x);
+            }
+          }
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
+
+      if (j > 0) {
+        mbar_wait(bar_o, ph ^ 1u);  // O += P_{j-1} V_{j-1} complete: O may be rescaled, P overwritten
+        tc_fence_after();
+        if (warp_valid && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < FA_HD / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_lane + FA_TMEM_O + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
+            tmem_st_32x32b_x32(t_lane + FA_TMEM_O + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+
+      // pass 2: p = exp2(x - m), row sum, P (bf16) -> shared memory (K-major SW128: chunk = key / 8, XOR row % 8)
+      float rs = 0.f;
+      if (warp_valid) {
+#pragma unroll
+        for (int c = 0; c < FA_BN / 32; ++c) {
+          if (c * 32 < ncols) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
+            tmem_ld_wait();
+            float pv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int col = c * 32 + k;
+              float x = __uint_as_float(r[k]) * sc2;
+              if (WAVLM) x = fmaf(gate, win[col], x);
+              float e = fast_exp2(x - m_new);
+              if (col >= ncols) e = 0.f;
+              pv[k] = e;
+              rs += e;
+            }
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              uint4 u;
+              u.x = pack_bf16x2(pv[k8 * 8 + 0], pv[k8 * 8 + 1]);
+              u.y = pack_bf16x2(pv[k8 * 8 + 2], pv[k8 * 8 + 3]);
+              u.z = pack_bf16x2(pv[k8 * 8 + 4], pv[k8 * 8 + 5]);
+              u.w = pack_bf16x2(pv[k8 * 8 + 6], pv[k8 * 8 + 7]);
+              const int ch = c * 4 + k8;
+              *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
+            }
+          } else {
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              const int ch = c * 4 + k8;
+              *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core's async proxy
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+
+    // ------------------------------ epilogue: O / l -> bf16 ------------------------------
+    mbar_wait(bar_o, (uint32_t)((nkv - 1) & 1));
+    tc_fence_after();
+    if (warp_valid) {
+      const float inv = 1.f / l_run;
+      bf16* orow = p.out + (int64_t)(r0 + qi) * p.d + h * FA_HD;
+#pragma unroll
+      for (int c = 0; c < FA_HD / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + FA_TMEM_O + c * 32, r);
+        tmem_ld_wait();
+        if (row_valid) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(r[k + 0]) * inv, __uint_as_float(r[k + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(r[k + 2]) * inv, __uint_as_float(r[k + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(r[k + 4]) * inv, __uint_as_float(r[k + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(r[k + 6]) * inv, __uint_as_float(r[k + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + k) = u;
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
+}  // namespace serenc

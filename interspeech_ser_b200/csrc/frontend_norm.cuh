@@ -84,44 +84,17 @@ constexpr int CONV0_TILE = 256;  // frames per block
 
 typedef UttSpan Conv0Utt;
 
-__device__ __forceinline__ void conv0_finish(float (&a)[16], int t, bool in_tile, const Conv0Utt& u,
-                                             bf16* __restrict__ out, const float2* s_g, const float2* s_be,
-                                             int lane) {
-  if (!in_tile) return;  // warp-uniform
-  uint32_t* orow = reinterpret_cast<uint32_t*>(out + (u.row0 + t) * CONV0_C);
-  if (t >= u.T0) {  // slot padding rows: zeros
-#pragma unroll
-    for (int i = 0; i < 8; ++i) orow[32 * i + lane] = 0u;
-    return;
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s += a[i];
-  const float mu = warp_sum(s) * (1.f / CONV0_C);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float d = a[i] - mu;
-    q += d * d;
-  }
-  const float rs = rsqrtf(warp_sum(q) * (1.f / CONV0_C) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
-    const float y0 = gelu_erf((a[2 * i] - mu) * rs * g.x + be.x);
-    const float y1 = gelu_erf((a[2 * i + 1] - mu) * rs * g.y + be.y);
-    orow[32 * i + lane] = pack_bf16x2(y0, y1);
-  }
-}
-
-__global__ void __launch_bounds__(256) conv0_ln_gelu_kernel(const float* __restrict__ wav,
-                                                             const Conv0Utt* __restrict__ utts,
-                                                             const float2* __restrict__ stats,  // nullptr: already normalised
-                                                             const float* __restrict__ w,       // [512][10]
-                                                             const float* __restrict__ bias,    // [512] or nullptr
-                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                             bf16* __restrict__ out) {
-  __shared__ float2 ws[CONV0_K][CONV0_C / 2];
+__global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __restrict__ wav,
+                                                                const Conv0Utt* __restrict__ utts,
+                                                                const float2* __restrict__ stats,  // nullptr: already normalised
+                                                                const float* __restrict__ w,       // [512][10]
+                                                                const float* __restrict__ bias,    // [512] or nullptr
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                bf16* __restrict__ out) {
+  // The 160 filter taps of a lane's 16 channels live in REGISTERS for the whole tile, so the inner loop is
+  // 160 FFMA + 10 broadcast shared-memory reads per frame (a shared-memory-resident filter made the kernel
+  // LDS-bound at ~1 TB/s of output).
+  __shared__ float ws[CONV0_C * CONV0_K];   // staging only: coalesced global read, then per-lane gather
   __shared__ float2 s_b[CONV0_C / 2], s_g[CONV0_C / 2], s_be[CONV0_C / 2];
   __shared__ float xs[CONV0_TILE * CONV0_S + CONV0_K];
 
@@ -130,10 +103,7 @@ __global__ void __launch_bounds__(256) conv0_ln_gelu_kernel(const float* __restr
   if (t0 >= u.slot) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  for (int i = threadIdx.x; i < CONV0_K * CONV0_C; i += blockDim.x) {
-    const int c = i / CONV0_K, j = i - c * CONV0_K;
-    reinterpret_cast<float*>(&ws[j][0])[c] = w[i];
-  }
+  for (int i = threadIdx.x; i < CONV0_K * CONV0_C; i += blockDim.x) ws[i] = w[i];
   for (int c = threadIdx.x; c < CONV0_C; c += blockDim.x) {
     reinterpret_cast<float*>(s_b)[c] = bias ? bias[c] : 0.f;
     reinterpret_cast<float*>(s_g)[c] = gamma[c];
@@ -152,30 +122,56 @@ __global__ void __launch_bounds__(256) conv0_ln_gelu_kernel(const float* __restr
   }
   __syncthreads();
 
+  float wr[16][CONV0_K];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < CONV0_K; ++j) {
+      wr[2 * i][j] = ws[(64 * i + 2 * lane) * CONV0_K + j];
+      wr[2 * i + 1][j] = ws[(64 * i + 2 * lane + 1) * CONV0_K + j];
+    }
+  }
+
   const int t_end = min(CONV0_TILE, u.slot - t0);
-  for (int f = warp * 2; f < t_end; f += 16) {
-    float a0[16], a1[16];
+  for (int f = warp; f < t_end; f += 8) {
+    const int t = t0 + f;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(out + (u.row0 + t) * CONV0_C);
+    if (t >= u.T0) {  // slot padding rows: zeros (warp-uniform)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) orow[32 * i + lane] = 0u;
+      continue;
+    }
+    float a[16];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float2 b = s_b[32 * i + lane];
-      a0[2 * i] = b.x; a0[2 * i + 1] = b.y;
-      a1[2 * i] = b.x; a1[2 * i + 1] = b.y;
+      a[2 * i] = b.x;
+      a[2 * i + 1] = b.y;
     }
 #pragma unroll
     for (int j = 0; j < CONV0_K; ++j) {
-      const float x0 = xs[f * CONV0_S + j];
-      const float x1 = xs[(f + 1) * CONV0_S + j];
+      const float xv = xs[f * CONV0_S + j];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 wv = ws[j][32 * i + lane];
-        a0[2 * i] = fmaf(wv.x, x0, a0[2 * i]);
-        a0[2 * i + 1] = fmaf(wv.y, x0, a0[2 * i + 1]);
-        a1[2 * i] = fmaf(wv.x, x1, a1[2 * i]);
-        a1[2 * i + 1] = fmaf(wv.y, x1, a1[2 * i + 1]);
-      }
+      for (int i = 0; i < 16; ++i) a[i] = fmaf(wr[i][j], xv, a[i]);
     }
-    conv0_finish(a0, t0 + f, f < t_end, u, out, s_g, s_be, lane);
-    conv0_finish(a1, t0 + f + 1, f + 1 < t_end, u, out, s_g, s_be, lane);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    const float mu = warp_sum(s) * (1.f / CONV0_C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float d = a[i] - mu;
+      q += d * d;
+    }
+    const float rs = rsqrtf(warp_sum(q) * (1.f / CONV0_C) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
+      const float y0 = gelu_erf_fast((a[2 * i] - mu) * rs * g.x + be.x);
+      const float y1 = gelu_erf_fast((a[2 * i + 1] - mu) * rs * g.y + be.y);
+      orow[32 * i + lane] = pack_bf16x2(y0, y1);
+    }
   }
 }
 

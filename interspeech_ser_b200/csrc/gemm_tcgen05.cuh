@@ -24,8 +24,10 @@
 //   * grouped positional Conv1d (k=128, groups=16; modeling_wavlm.py:48-90): s = 1, 128 taps, the group picks
 //     the column block. W is packed [N, tap*C_pad + c] to match.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..11 = epilogue. Warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per thread, the only
+// Warp roles (384 threads): warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = MMA issuer, warp 10 = TMEM
+// allocator. (The single-thread producer / issuer roles sit on the HIGHEST warp ids: the SM's issue arbiter
+// favours higher warp ids, and a GELU-heavy epilogue warp must never delay a tcgen05.mma or TMA issue.)
+// Epilogue warp w reads TMEM lanes 32*(w%4) .. +31 (one accumulator row per thread, the only
 // shape tcgen05.ld offers) for its half of the tile's columns, transposes each 32x32 block through a padded
 // shared-memory tile and then touches global memory with lanes running along a row: bias / GELU / residual /
 // stores are all 128-byte-coalesced (the row-per-thread layout would cost 32 sectors per request).
@@ -38,6 +40,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_WARP_TMA = 8, GEMM_WARP_MMA = 9, GEMM_WARP_ALLOC = 10;
 constexpr int GEMM_ST_LD = 36;  // staging row stride in words: 16-byte aligned rows, conflict-free 128-bit accesses
 constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * GEMM_ST_LD * 4;  // per-warp padded 32x32 fp32 transpose tile
 constexpr int GEMM2_BN = 256;     // 2-CTA kernel: tile is 256 (M, 128 per CTA) x 256 (N, W rows split 128 per CTA)
@@ -103,9 +106,13 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
 // Epilogue of one warp for its 32 rows x NCOLS columns of an accumulator.
 //   t_addr : TMEM address of (lane quarter, first column)   row0 : first of the warp's 32 rows
 //   n0     : first column (within the group) of the warp's column range
+//   ready  : mbarrier (and parity) signalled when the accumulator is complete. The wait sits INSIDE this function so
+//            that the first block of residual values is already in flight while the MMAs are still running; after
+//            that the residual of block c+1 is fetched while block c is processed (the residual stream is fp32 in
+//            HBM/L2: ~1 us away, and the out-projection / FC2 epilogues would otherwise be latency-bound).
 template <int NCOLS>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* st, uint32_t t_addr, int64_t row0, int g,
-                                                   int n0, int lane) {
+                                                   int n0, int lane, uint64_t* ready, uint32_t ready_parity) {
   const int sr = lane >> 3;       // coalesced phase: sub-row 0..3
   const int c4 = (lane & 7) * 4;  // coalesced phase: 4 consecutive columns
   int64_t orow[8];                // output rows this lane touches in the coalesced phase
@@ -115,12 +122,28 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
     orow[i] = -1;
     if (r < p.M) orow[i] = p.rowmap ? (int64_t)__ldg(p.rowmap + r) : r;
   }
+  float4 q[8], qn[8];
+  auto fetch_resid = [&](float4 (&dst)[8], int col0) {
+    const int col = col0 + c4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < p.n_per_group && orow[i] >= 0)
+        dst[i] = *reinterpret_cast<const float4*>(p.resid + orow[i] * p.ld_f32 + g * p.n_per_group + col);
+    }
+  };
+  if (p.resid) fetch_resid(q, n0);
+
+  mbar_wait(ready, ready_parity);
+  tc_fence_after();
+
 #pragma unroll 1
   for (int c = 0; c < NCOLS / 32; ++c) {
     const int col0 = n0 + c * 32;
     if (col0 >= p.n_per_group) break;  // warp-uniform
     uint32_t r[32];
     tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+    if (p.resid && c + 1 < NCOLS / 32) fetch_resid(qn, col0 + 32);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
@@ -131,16 +154,6 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
       const int gcol = g * p.n_per_group + col;
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-      // residual loads first, all 8 in flight (in-place update: a load behind a possibly aliasing store
-      // would serialise on the ~1 us DRAM latency)
-      float4 q[8];
-      if (p.resid) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          q[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (orow[i] >= 0) q[i] = *reinterpret_cast<const float4*>(p.resid + orow[i] * p.ld_f32 + gcol);
-        }
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (orow[i] < 0) continue;
@@ -160,6 +173,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
           *reinterpret_cast<uint2*>(p.out_bf16 + orow[i] * p.ld_bf16 + gcol) = u;
         }
       }
+    }
+    if (p.resid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = qn[i];
     }
     __syncwarp();
   }
@@ -188,12 +205,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == GEMM_WARP_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -204,7 +221,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == GEMM_WARP_ALLOC) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -215,7 +232,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;
 
-  if (warp == 0) {
+  if (warp == GEMM_WARP_TMA) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -243,7 +260,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == GEMM_WARP_MMA) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
@@ -277,19 +294,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // ------------------------------ epilogue ------------------------------
     const int ew = warp & 3;                 // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;        // which half of the tile's columns
-    float* st = staging + (warp - 4) * (32 * GEMM_ST_LD);
+    const int half = warp >> 2;        // which half of the tile's columns
+    float* st = staging + warp * (32 * GEMM_ST_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-      gemm_epilogue_warp<BN / 2>(p, st, t_addr, (int64_t)tc.m_t * GEMM_BM + ew * 32, tc.g, tc.n_t * BN + half * (BN / 2), lane);
+      gemm_epilogue_warp<BN / 2>(p, st, t_addr, (int64_t)tc.m_t * GEMM_BM + ew * 32, tc.g, tc.n_t * BN + half * (BN / 2), lane,
+                                 &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -301,7 +317,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == GEMM_WARP_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -333,12 +349,12 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == GEMM_WARP_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);   // leader's producer arrives (expect_tx covers both CTAs' TMA bytes)
       mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit from the leader
@@ -349,7 +365,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == GEMM_WARP_ALLOC) {
     tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish_2cta();
   }
@@ -360,7 +376,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;   // tiles_m counts 256-row tiles here
 
-  if (warp == 0) {
+  if (warp == GEMM_WARP_TMA) {
     // ------------------------------ TMA producer (both CTAs) ------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -389,7 +405,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == GEMM_WARP_MMA) {
     // ------------------------------ MMA issuer (leader CTA only) ------------------------------
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
@@ -422,20 +438,18 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     const int ew = warp & 3;
-    const int half = (warp - 4) >> 2;
-    float* st = staging + (warp - 4) * (32 * GEMM_ST_LD);
+    const int half = warp >> 2;
+    float* st = staging + warp * (32 * GEMM_ST_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const TileCoord tc = decode_tile(p, tile);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t row0 = (int64_t)tc.m_t * (2 * GEMM_BM) + (int64_t)rank * GEMM_BM + ew * 32;
-      gemm_epilogue_warp<BN / 2>(p, st, t_addr, row0, tc.g, tc.n_t * BN + half * (BN / 2), lane);
+      gemm_epilogue_warp<BN / 2>(p, st, t_addr, row0, tc.g, tc.n_t * BN + half * (BN / 2), lane, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
@@ -447,7 +461,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();   // no CTA of the pair may exit while the other can still signal it
-  if (warp == 2) {
+  if (warp == GEMM_WARP_ALLOC) {
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "frontend_norm.cuh"
 #include "gemm_tcgen05.cuh"
@@ -104,6 +105,7 @@ struct serenc_handle {
   std::atomic<long long> launches{0};
   bool prof = false;
   bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
+  bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: head_dim-64 attention on the mma.sync kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
 };
@@ -440,9 +442,23 @@ int launch_attn_hd(const AttnParams& p, bool wavlm, int tmax, int heads, int bat
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, double alg_flops, cudaStream_t st) {
+int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, int64_t sum_rows, double alg_flops,
+                cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
   ProfScope ps(h, SERENC_PROF_ATTENTION, 1, alg_flops, 0.0, st);
+  if (h->head_dim == 64 && !h->force_mma_sync_attn) {
+    // tcgen05 path: Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
+    CUtensorMap tmq, tmkv;
+    SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
+    SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
+    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
+    if (wavlm)
+      attention_tc_kernel<true><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, p);
+    else
+      attention_tc_kernel<false><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, p);
+    SERENC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (h->head_dim) {
     case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
     case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
@@ -612,6 +628,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->num_sms = prop.multiProcessorCount;
   h->head_dim = hd;
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   *out = h;
 
   int st = 0;
@@ -661,6 +678,8 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
   }
   if (st) {
     serenc_destroy(h);
@@ -930,7 +949,7 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
       p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
-      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, attn_flops, st));
+      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
     {
       GemmCall g = linear_call(b.att, sumT, d, l.w_o, d);
@@ -1465,5 +1484,5 @@ extern "C" int serenc_op_attention(serenc_handle* h, const void* qkv, const int6
   p.hln = reinterpret_cast<const bf16*>(hln);
   const LayerW& l = h->L[wavlm ? layer : 0];
   p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
-  return launch_attn(h, p, wavlm != 0, tmax, batch, 0.0, st);
+  return launch_attn(h, p, wavlm != 0, tmax, batch, frame_offsets[batch], 0.0, st);
 }
