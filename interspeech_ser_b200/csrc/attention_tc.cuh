@@ -65,7 +65,7 @@ template <bool WAVLM>
 __global__ void __launch_bounds__(FA_THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t fa_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(fa_smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + FA_Q_BYTES;
   uint8_t* sV = sK + FA_KV_BYTES;

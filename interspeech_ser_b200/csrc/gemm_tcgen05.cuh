@@ -192,7 +192,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -333,7 +333,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = GEMM2_BN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
