@@ -32,9 +32,11 @@ WAVE_STD = 0.0886  # MSP-Podcast corpus std (reference: benchmark/model/cat_ser/
 
 WORKLOADS = {
     # name: (config, utterance seconds, per-GPU batch, description)
-    "wavlm-large": ("microsoft/wavlm-large", 4.0, 128,
+    # 142 x 199 frames = 28 258 rows = 111 row-tiles of 256: every transformer GEMM is then a whole number of
+    # waves over the 74 CTA pairs (111 x {4, 12, 16} n-tiles = {6, 18, 24} x 74) — the scheduler's frame budget.
+    "wavlm-large": ("microsoft/wavlm-large", 4.0, 142,
                     "WavLM-large (random-init) embedding extraction, 4 s synthetic 16 kHz utterances "
-                    "(BASELINE configs[0] utterance shape), batch 128 per GPU"),
+                    "(BASELINE configs[0] utterance shape), batch 142 per GPU"),
     "wavlm-large-c1": ("microsoft/wavlm-large", 4.0, 8,
                        "WavLM-large (random-init) embedding extraction, batch 8 x 4 s synthetic 16 kHz utterances (BASELINE configs[0])"),
     "whisper-large-v3": ("openai/whisper-large-v3", 30.0, 32,

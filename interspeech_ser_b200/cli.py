@@ -33,7 +33,7 @@ def build_parser(whisper: bool) -> argparse.ArgumentParser:
     p.add_argument("--use_average", type=str, default="n")
     # additions
     p.add_argument("--random_init", action="store_true", help="random weights (no checkpoint available offline)")
-    p.add_argument("--frame_budget", type=int, default=32768, help="max frames per packed batch")
+    p.add_argument("--frame_budget", type=int, default=28416, help="max frames per packed batch (111 x 256: whole GEMM waves)")
     p.add_argument("--skip_existing", action="store_true", help="resume: skip files whose .pt already exists")
     p.add_argument("--pooled_path", type=str, default="", help="also save masked-mean pooled embeddings {names, embeddings[N, D]}")
     if not whisper:

@@ -235,7 +235,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(bar_s, ph);
       tc_fence_after();
 
-      // pass 1: row maximum of  s * scale * log2e + gate * bias
+      // pass 1: row maximum of  x = s * scale * log2e (+ gate * bias). Without bias the maximum is taken on the
+      // raw scores (scale > 0). Ragged last block: columns >= ncols are excluded; full blocks carry no compares.
+      const bool full = (ncols == FA_BN);   // CTA-uniform
       float mx = -INFINITY;
       if (warp_valid) {
 #pragma unroll
@@ -244,15 +246,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
             tmem_ld_wait();
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (full) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const int col = c * 32 + k;
-              float x = __uint_as_float(r[k]) * sc2;
-              if (WAVLM) x = fmaf(gate, win[col], x);
-              if (col < ncols) mx = fmaxf(mx, x);
+              for (int k = 0; k < 32; ++k) {
+                float x = __uint_as_float(r[k]);
+                if (WAVLM) x = fmaf(gate, win[c * 32 + k], x * sc2);
+                m4[k & 3] = fmaxf(m4[k & 3], x);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                float x = __uint_as_float(r[k]);
+                if (WAVLM) x = fmaf(gate, win[c * 32 + k], x * sc2);
+                if (c * 32 + k < ncols) m4[k & 3] = fmaxf(m4[k & 3], x);
+              }
             }
+            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
           }
         }
+        if (!WAVLM) mx *= sc2;
       }
       const float m_new = fmaxf(m_run, mx);
       const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
@@ -277,30 +290,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // pass 2: p = exp2(x - m), row sum, P (bf16) -> shared memory (K-major SW128: chunk = key / 8, XOR row % 8)
       float rs = 0.f;
       if (warp_valid) {
+        const float neg_m = -m_new;
 #pragma unroll
         for (int c = 0; c < FA_BN / 32; ++c) {
           if (c * 32 < ncols) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
             tmem_ld_wait();
-            float pv[32];
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              const int col = c * 32 + k;
-              float x = __uint_as_float(r[k]) * sc2;
-              if (WAVLM) x = fmaf(gate, win[col], x);
-              float e = fast_exp2(x - m_new);
-              if (col >= ncols) e = 0.f;
-              pv[k] = e;
-              rs += e;
+              float x = __uint_as_float(r[k]);
+              float e;
+              if (WAVLM) e = fast_exp2(fmaf(gate, win[c * 32 + k], fmaf(x, sc2, neg_m)));
+              else e = fast_exp2(fmaf(x, sc2, neg_m));
+              if (!full && c * 32 + k >= ncols) e = 0.f;
+              s4[k & 3] += e;
+              r[k] = __float_as_uint(e);
             }
+            rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
               uint4 u;
-              u.x = pack_bf16x2(pv[k8 * 8 + 0], pv[k8 * 8 + 1]);
-              u.y = pack_bf16x2(pv[k8 * 8 + 2], pv[k8 * 8 + 3]);
-              u.z = pack_bf16x2(pv[k8 * 8 + 4], pv[k8 * 8 + 5]);
-              u.w = pack_bf16x2(pv[k8 * 8 + 6], pv[k8 * 8 + 7]);
+              u.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]), __uint_as_float(r[k8 * 8 + 1]));
+              u.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]), __uint_as_float(r[k8 * 8 + 3]));
+              u.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]), __uint_as_float(r[k8 * 8 + 5]));
+              u.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]), __uint_as_float(r[k8 * 8 + 7]));
               const int ch = c * 4 + k8;
               *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
             }

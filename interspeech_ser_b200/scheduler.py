@@ -41,9 +41,12 @@ class Batch:
     flops: float
 
 
-def make_batches(cfg: EncoderConfig, lengths: Sequence[int], frame_budget: int = 32768, max_batch: int = 1024,
+def make_batches(cfg: EncoderConfig, lengths: Sequence[int], frame_budget: int = 28416, max_batch: int = 1024,
                  max_spread: float = 0.0) -> List[Batch]:
     """Sort by length and cut into batches of at most `frame_budget` frames / `max_batch` utterances.
+    The default budget, 28 416 = 111 x 256 frames, makes the row-tile count of the 256 x 256 CTA-pair GEMM a
+    multiple of 37, so that every transformer GEMM (4 / 12 / 16 column tiles) is a whole number of waves over the
+    74 CTA pairs of a B200.
     max_spread > 0 additionally closes a batch when the longest/shortest frame ratio would exceed 1 + max_spread
     (length bucketing; with the packed layout padding costs nothing, so spread only matters for attention tiles).
     Utterances too short to yield a frame are rejected up front (HF would raise inside the conv stack)."""
