@@ -207,6 +207,12 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// Rows per warp: narrow rows give a warp too little to do per trip to HBM, so it keeps several rows in flight.
+template <int NV>
+struct LnRows {
+  static constexpr int RPW = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
+};
+
 template <int NV, typename TIn, typename TOut, bool GELU>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
                                                               TOut* __restrict__ out, int64_t ld_out,
@@ -214,44 +220,62 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
                                                               const float* __restrict__ beta, int64_t rows,
                                                               const int32_t* __restrict__ in_rowmap,
                                                               const int32_t* __restrict__ out_rowmap, float eps) {
+  constexpr int RPW = LnRows<NV>::RPW;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int64_t irow = in_rowmap ? (int64_t)in_rowmap[row] : row;
-  const int64_t orow = out_rowmap ? (int64_t)out_rowmap[row] : row;
-  if (irow < 0 || orow < 0) return;
-  const TIn* x = in + irow * ld_in;
-  float4 v[NV];
-  float s = 0.f;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
+  int64_t irow[RPW], orow[RPW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    v[i] = load4<TIn>(x + (lane + 32 * i) * 4);
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r;
+    irow[r] = orow[r] = -1;
+    if (row < rows) {
+      irow[r] = in_rowmap ? (int64_t)in_rowmap[row] : row;
+      orow[r] = out_rowmap ? (int64_t)out_rowmap[row] : row;
+      if (irow[r] < 0 || orow[r] < 0) irow[r] = orow[r] = -1;
+    }
+  }
+  float4 v[RPW][NV];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      v[r][i] = irow[r] >= 0 ? load4<TIn>(in + irow[r] * ld_in + (lane + 32 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   constexpr float invC = 1.f / (128.f * NV);
-  const float mu = warp_sum(s) * invC;
-  float q = 0.f;
+  float mu[RPW], rs[RPW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
-    q += (a * a + b * b) + (c * c + d * d);
+  for (int r = 0; r < RPW; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    mu[r] = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[r][i].x - mu[r], b = v[r][i].y - mu[r], c = v[r][i].z - mu[r], d = v[r][i].w - mu[r];
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    rs[r] = rsqrtf(warp_sum(q) * invC + eps);
   }
-  const float rs = rsqrtf(warp_sum(q) * invC + eps);
-  TOut* y = out + orow * ld_out;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
-    float4 o;
-    o.x = (v[i].x - mu) * rs * g.x + be.x;
-    o.y = (v[i].y - mu) * rs * g.y + be.y;
-    o.z = (v[i].z - mu) * rs * g.z + be.z;
-    o.w = (v[i].w - mu) * rs * g.w + be.w;
-    if (GELU) {
-      o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (orow[r] < 0) continue;
+      float4 o;
+      o.x = (v[r][i].x - mu[r]) * rs[r] * g.x + be.x;
+      o.y = (v[r][i].y - mu[r]) * rs[r] * g.y + be.y;
+      o.z = (v[r][i].z - mu[r]) * rs[r] * g.z + be.z;
+      o.w = (v[r][i].w - mu[r]) * rs[r] * g.w + be.w;
+      if (GELU) {
+        o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w);
+      }
+      store4<TOut>(out + orow[r] * ld_out + c, o);
     }
-    store4<TOut>(y + c, o);
   }
 }
 

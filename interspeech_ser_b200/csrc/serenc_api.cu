@@ -395,12 +395,12 @@ int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64
                 int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st) {
   if (rows <= 0) return 0;
   const int nv = cols / 128;
-  const dim3 grid((unsigned)ceil_div64(rows, 8)), block(256);
+  const dim3 block(256);
   ProfScope ps(h, SERENC_PROF_LAYERNORM, 1, 0.0, (double)rows * cols * (sizeof(TIn) + sizeof(TOut)), st);
-#define SERENC_LN_CASE(NV)                                                                                       \
-  case NV:                                                                                                       \
-    layernorm_rows_kernel<NV, TIn, TOut, GELU><<<grid, block, 0, st>>>(in, ld_in, out, ld_out, g, b, rows, in_map, \
-                                                                       out_map, eps);                            \
+#define SERENC_LN_CASE(NV)                                                                                         \
+  case NV:                                                                                                         \
+    layernorm_rows_kernel<NV, TIn, TOut, GELU><<<dim3((unsigned)ceil_div64(rows, 8 * LnRows<NV>::RPW)), block, 0, st>>>( \
+        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps);                                                 \
     break;
   switch (nv) {
     SERENC_LN_CASE(1)

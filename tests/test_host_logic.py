@@ -141,3 +141,15 @@ def test_cli_parsers_keep_reference_flags():
     for whisper in (False, True):
         a = build_parser(whisper).parse_args([])
         assert (a.seed, a.ssl_type, a.save_path, a.wav_dir, a.num_workers, a.n_layer, a.use_average) == (7, "wavlm-large", "./", "./", 4, -1, "n")
+
+
+def test_epilogue_gelu_constants_are_exact_to_roundoff():
+    """The polynomial-exp2 erfc used by the CUDA epilogues (csrc/common.cuh) against the exact erf GELU."""
+    import re
+    from oracle import gelu_fit
+    assert gelu_fit.max_error() < 1e-6
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interspeech_ser_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_erf_fast(float x)"):]
+    body = body[:body.index("return fmaf(-a, e, hx + a);")]
+    consts = [float(v) for v in re.findall(r"(-?\d\.\d{9}e[+-]\d\d)f", body)]
+    assert consts == list(reversed(gelu_fit.COEFFS))      # Horner order in the kernel = descending powers
