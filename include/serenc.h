@@ -178,6 +178,9 @@ int serenc_set_profiling(serenc_handle* h, int enable);
 /* Synchronises and sums, per class, device milliseconds / algorithmic FLOPs / algorithmic bytes / launches. */
 int serenc_get_profile(serenc_handle* h, int n_classes, double* ms, double* flops, double* bytes, int64_t* launches);
 
+/* Debug: per-tile clock64 stamps of CTA 0 of the CTA-pair GEMM are written to dev_buf ([tiles][8] int64); NULL disables. */
+int serenc_debug_gemm_trace(serenc_handle* h, void* dev_buf);
+
 /* ---- diagnostic entry points (op-level known-answer tests; not needed by an integrator) ------------ */
 
 /* out = epilogue(A[M,K] * W[N,K]^T): bf16 operands, fp32 accumulate. a_row_stride (elements) may be smaller

@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "serenc_encode_w2v", "serenc_unpack_frames", "serenc_logmel", "serenc_whisper_workspace_bytes",
     "serenc_encode_whisper", "serenc_op_gemm", "serenc_op_gemm_grouped", "serenc_op_layernorm",
     "serenc_op_attention", "serenc_wavlm_bucket", "serenc_launch_count", "serenc_set_profiling", "serenc_get_profile",
+    "serenc_debug_gemm_trace",
 ]
 
 
@@ -80,6 +81,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "serenc_op_layernorm": (C.c_int, [vp, vp, i64, C.c_int, vp, vp, C.c_float, C.c_int, vp, vp, vp]),
             "serenc_op_attention": (C.c_int, [vp, vp, pi64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
             "serenc_launch_count": (i64, [vp]),
+            "serenc_debug_gemm_trace": (C.c_int, [vp, vp]),
             "serenc_set_profiling": (C.c_int, [vp, C.c_int]),
             "serenc_get_profile": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), pi64]),
         }

@@ -34,6 +34,7 @@ constexpr int FA_WIN = FA_BM + FA_BN - 1;       // bias window entries per (q ti
 constexpr int FA_SMEM_BYTES = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + 8 * FA_HD * 4 /*gate weights*/ +
                               2 * 192 * 4 /*bias windows*/ + 64 /*barriers*/ + 1024;
 constexpr int FA_TMEM_COLS = 128;
+constexpr uint32_t FA_WAIT_HINT_NS = 2000;   // softmax threads sleep (NANOSLEEP.SYNCS) instead of spinning on S / O barriers
 constexpr int FA_TMEM_S = 0, FA_TMEM_O = 64;
 
 // MN-major (N contiguous), 128B-swizzled B operand: 8-row (K) groups are 1024 B apart
@@ -232,7 +233,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         softmax_group_sync();
       }
-      mbar_wait(bar_s, ph);
+      mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_s, ph);
       tc_fence_after();
 
       // pass 1: row maximum of  x = s * scale * log2e (+ gate * bias). Without bias the maximum is taken on the
@@ -271,7 +272,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
 
       if (j > 0) {
-        mbar_wait(bar_o, ph ^ 1u);  // O += P_{j-1} V_{j-1} complete: O may be rescaled, P overwritten
+        mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_o, ph ^ 1u);  // O += P_{j-1} V_{j-1} complete: O may be rescaled, P overwritten
         tc_fence_after();
         if (warp_valid && !__all_sync(0xffffffffu, alpha == 1.0f)) {
 #pragma unroll
@@ -336,7 +337,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
 
     // ------------------------------ epilogue: O / l -> bf16 ------------------------------
-    mbar_wait(bar_o, (uint32_t)((nkv - 1) & 1));
+    mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_o, (uint32_t)((nkv - 1) & 1));
     tc_fence_after();
     if (warp_valid) {
       const float inv = 1.f / l_run;

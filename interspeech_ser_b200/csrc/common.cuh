@@ -108,7 +108,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
-  // suspend-time hint (ns): a waiting thread sleeps in hardware instead of burning issue slots on a spin loop
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+// try_wait with a suspend-time hint (ns): ptxas turns a failed probe into NANOSLEEP.SYNCS <hint>, i.e. the thread
+// stops burning issue slots — at the price of wake-up latency. Only for waits that are long and not on the
+// critical path (the attention kernel's 128 softmax threads), never for the GEMM pipeline.
+template <uint32_t HINT_NS>
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -116,7 +132,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(HINT_NS)
       : "memory");
   return done != 0;
 }
@@ -125,19 +141,34 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __noinline__ void mbar_watchdog_trap(uint32_t parity) {
+  printf("serenc: mbarrier watchdog (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if SERENC_WATCHDOG
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0xffu) == 0 && global_timer_ns() - t0 > 4000000000ull) {   // 4 s: a protocol bug, not a wait
-      printf("serenc: mbarrier watchdog (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (((++spins) & 0xfffu) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_watchdog_trap(parity);  // 4 s: a bug
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
+}
+template <uint32_t HINT_NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if SERENC_WATCHDOG
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint<HINT_NS>(bar, parity)) {
+    if (((++spins) & 0xffu) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_watchdog_trap(parity);
+  }
+#else
+  while (!mbar_try_wait_hint<HINT_NS>(bar, parity)) {
   }
 #endif
 }

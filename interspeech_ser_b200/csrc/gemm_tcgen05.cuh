@@ -64,6 +64,7 @@ struct GemmParams {
   int64_t ld_bf16;
   const int32_t* rowmap; // [M] -> output row, <0 = skip; nullptr = identity
   int act;               // 0 = none, 1 = exact GELU (applied before the residual add)
+  long long* trace;      // debug: per-tile clock64 stamps of CTA 0 ([tile][8]); nullptr in production
 };
 
 template <int BN>
@@ -106,21 +107,94 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
 // Epilogue of one warp for its 32 rows x NCOLS columns of an accumulator.
 //   t_addr : TMEM address of (lane quarter, first column)   row0 : first of the warp's 32 rows
 //   n0     : first column (within the group) of the warp's column range
-//   ready  : mbarrier (and parity) signalled when the accumulator is complete. The wait sits INSIDE this function so
-//            that the first block of residual values is already in flight while the MMAs are still running; after
-//            that the residual of block c+1 is fetched while block c is processed (the residual stream is fp32 in
-//            HBM/L2: ~1 us away, and the out-projection / FC2 epilogues would otherwise be latency-bound).
-template <int NCOLS>
+//   ready  : mbarrier (and parity) signalled when the accumulator is complete.
+//
+// Measured with per-tile clock stamps (tests/trace_gemm.py): the epilogue is bound by on-chip traffic, not by
+// instructions — TMEM reads (~64 B/clk/SM) plus the shared-memory transpose. Two paths keep it below the
+// K = 1024 mainloop (~10 k cycles per 128 x 256 accumulator):
+//   * bf16-only outputs (QKV, FC1, conv layers): bias + GELU are applied in the row-per-thread layout tcgen05.ld
+//     delivers, the result is packed to bf16 and only 64 B per row go through an XOR-swizzled staging tile
+//     (conflict-free 128-bit writes by row and reads by 4-lane row segments); stores are 16 B per lane.
+//   * fp32 outputs (residual stream): fp32 staging with 36-word rows; the residual values of block c+1 are
+//     fetched while block c is processed, the first block before the accumulator is even ready.
+// In both paths the TMEM load of the next 32-column block is issued before the current block is processed.
+template <int NCOLS, bool EPI_BF16>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* st, uint32_t t_addr, int64_t row0, int g,
-                                                   int n0, int lane, uint64_t* ready, uint32_t ready_parity) {
+                                                   int n0, int lane, uint64_t* ready, uint32_t ready_parity,
+                                                   long long* trace_after_wait = nullptr) {
+  constexpr int NCH = NCOLS / 32;
+
+  if constexpr (EPI_BF16) {
+    // coalesced phase: lane -> (row 8*i + lane/4, 16-byte segment lane%4 = 8 bf16 columns)
+    const int sr = lane >> 2, sc = lane & 3;
+    int64_t orow[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t r = row0 + 8 * i + sr;
+      orow[i] = -1;
+      if (r < p.M) orow[i] = p.rowmap ? (int64_t)__ldg(p.rowmap + r) : r;
+    }
+    uint4* st4 = reinterpret_cast<uint4*>(st);   // [32 rows][4 chunks of 16 B], chunk index XOR-swizzled by row
+    mbar_wait(ready, ready_parity);
+    tc_fence_after();
+    if (trace_after_wait) *trace_after_wait = clock64();
+    uint32_t ra[32], rb[32];
+    if (n0 < p.n_per_group) tmem_ld_32x32b_x32(t_addr, ra);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 < p.n_per_group) {  // warp-uniform
+        uint32_t (&r)[32] = (c & 1) ? rb : ra;
+        tmem_ld_wait();
+        if (c + 1 < NCH && col0 + 32 < p.n_per_group) tmem_ld_32x32b_x32(t_addr + (uint32_t)((c + 1) * 32), (c & 1) ? ra : rb);
+        const int gcol0 = g * p.n_per_group + col0;
+        const bool tail = (col0 + 32 > p.n_per_group);   // only multiples of 8 columns are valid (checked on the host)
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[k8 * 8 + e]);
+          if (p.bias && !(tail && col0 + k8 * 8 >= p.n_per_group)) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + k8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol0 + k8 * 8 + 4));
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
+          }
+          uint4 u;
+          u.x = pack_bf16x2(v[0], v[1]);
+          u.y = pack_bf16x2(v[2], v[3]);
+          u.z = pack_bf16x2(v[4], v[5]);
+          u.w = pack_bf16x2(v[6], v[7]);
+          st4[lane * 4 + (k8 ^ ((lane >> 1) & 3))] = u;
+        }
+        __syncwarp();
+        const int col = col0 + sc * 8;
+        if (col < p.n_per_group) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = 8 * i + sr;
+            const uint4 u = st4[rl * 4 + (sc ^ ((rl >> 1) & 3))];
+            if (orow[i] >= 0) *reinterpret_cast<uint4*>(p.out_bf16 + orow[i] * p.ld_bf16 + g * p.n_per_group + col) = u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  } else {
+  // ---------------- fp32 / residual path ----------------
   const int sr = lane >> 3;       // coalesced phase: sub-row 0..3
   const int c4 = (lane & 7) * 4;  // coalesced phase: 4 consecutive columns
-  int64_t orow[8];                // output rows this lane touches in the coalesced phase
+  int32_t orow[8];                // output rows this lane touches in the coalesced phase (< 2^31 rows)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t r = row0 + 4 * i + sr;
     orow[i] = -1;
-    if (r < p.M) orow[i] = p.rowmap ? (int64_t)__ldg(p.rowmap + r) : r;
+    if (r < p.M) orow[i] = p.rowmap ? __ldg(p.rowmap + r) : (int32_t)r;
   }
   float4 q[8], qn[8];
   auto fetch_resid = [&](float4 (&dst)[8], int col0) {
@@ -129,63 +203,66 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
     for (int i = 0; i < 8; ++i) {
       dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col < p.n_per_group && orow[i] >= 0)
-        dst[i] = *reinterpret_cast<const float4*>(p.resid + orow[i] * p.ld_f32 + g * p.n_per_group + col);
+        dst[i] = *reinterpret_cast<const float4*>(p.resid + (int64_t)orow[i] * p.ld_f32 + g * p.n_per_group + col);
     }
   };
   if (p.resid) fetch_resid(q, n0);
 
   mbar_wait(ready, ready_parity);
   tc_fence_after();
+  if (trace_after_wait) *trace_after_wait = clock64();
 
 #pragma unroll 1
-  for (int c = 0; c < NCOLS / 32; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const int col0 = n0 + c * 32;
-    if (col0 >= p.n_per_group) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
-    if (p.resid && c + 1 < NCOLS / 32) fetch_resid(qn, col0 + 32);
-    tmem_ld_wait();
+    if (col0 < p.n_per_group) {  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+      if (p.resid && c + 1 < NCH) fetch_resid(qn, col0 + 32);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<uint4*>(st + lane * GEMM_ST_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    __syncwarp();
-    const int col = col0 + c4;
-    if (col < p.n_per_group) {
-      const int gcol = g * p.n_per_group + col;
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(st + lane * GEMM_ST_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      __syncwarp();
+      const int col = col0 + c4;
+      if (col < p.n_per_group) {
+        const int gcol = g * p.n_per_group + col;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (orow[i] < 0) continue;
-        float4 v = *reinterpret_cast<const float4*>(st + (4 * i + sr) * GEMM_ST_LD + c4);
-        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-        if (p.act == 1) {
-          v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
-        }
-        if (p.resid) {
-          v.x += q[i].x; v.y += q[i].y; v.z += q[i].z; v.w += q[i].w;
-        }
-        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + orow[i] * p.ld_f32 + gcol) = v;
-        if (p.out_bf16) {
-          uint2 u;
-          u.x = pack_bf16x2(v.x, v.y);
-          u.y = pack_bf16x2(v.z, v.w);
-          *reinterpret_cast<uint2*>(p.out_bf16 + orow[i] * p.ld_bf16 + gcol) = u;
+        for (int i = 0; i < 8; ++i) {
+          if (orow[i] < 0) continue;
+          float4 v = *reinterpret_cast<const float4*>(st + (4 * i + sr) * GEMM_ST_LD + c4);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (p.act == 1) {
+            v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
+          }
+          if (p.resid) {
+            v.x += q[i].x; v.y += q[i].y; v.z += q[i].z; v.w += q[i].w;
+          }
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)orow[i] * p.ld_f32 + gcol) = v;
+          if (p.out_bf16) {
+            uint2 u;
+            u.x = pack_bf16x2(v.x, v.y);
+            u.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)orow[i] * p.ld_bf16 + gcol) = u;
+          }
         }
       }
-    }
-    if (p.resid) {
+      if (p.resid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = qn[i];
+        for (int i = 0; i < 8; ++i) q[i] = qn[i];
+      }
+      __syncwarp();
     }
-    __syncwarp();
+  }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // single-CTA kernel: 128 x BN tiles
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool EPI_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                          const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -304,8 +381,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-      gemm_epilogue_warp<BN / 2>(p, st, t_addr, (int64_t)tc.m_t * GEMM_BM + ew * 32, tc.g, tc.n_t * BN + half * (BN / 2), lane,
-                                 &tfull_bar[acc], acc_phase);
+      gemm_epilogue_warp<BN / 2, EPI_BF16>(p, st, t_addr, (int64_t)tc.m_t * GEMM_BM + ew * 32, tc.g,
+                                           tc.n_t * BN + half * (BN / 2), lane, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -326,6 +403,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
 // ------------------------------------------------------------------------------------------------
 // CTA-pair kernel: 256 x 256 tiles, tcgen05.mma.cta_group::2
 // ------------------------------------------------------------------------------------------------
+template <bool EPI_BF16>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -413,13 +491,17 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
+        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == 0 && p.trace && blockIdx.x == 0) p.trace[it * 8 + 2] = clock64();
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
@@ -434,6 +516,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
           }
         }
         umma_commit_2cta(&tfull_bar[acc]);  // accumulator complete, signalled to both CTAs' epilogues
+        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 3] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -445,13 +528,17 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
     float* st = staging + warp * (32 * GEMM_ST_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const TileCoord tc = decode_tile(p, tile);
       const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
       const int64_t row0 = (int64_t)tc.m_t * (2 * GEMM_BM) + (int64_t)rank * GEMM_BM + ew * 32;
-      gemm_epilogue_warp<BN / 2>(p, st, t_addr, row0, tc.g, tc.n_t * BN + half * (BN / 2), lane, &tfull_bar[acc], acc_phase);
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[it * 8 + 4] = clock64();
+      gemm_epilogue_warp<BN / 2, EPI_BF16>(p, st, t_addr, row0, tc.g, tc.n_t * BN + half * (BN / 2), lane, &tfull_bar[acc],
+                                           acc_phase, (p.trace && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace + it * 8 + 5 : nullptr);
       tc_fence_before();
       __syncwarp();
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[it * 8 + 6] = clock64();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;

@@ -104,6 +104,7 @@ struct serenc_handle {
   // launch accounting / optional per-class device timing (bench.py's roofline numbers)
   std::atomic<long long> launches{0};
   bool prof = false;
+  long long* gemm_trace = nullptr;  // debug: device buffer for per-tile clock stamps of the CTA-pair GEMM (serenc_debug_gemm_trace)
   bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
   bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: head_dim-64 attention on the mma.sync kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
@@ -271,6 +272,7 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   p.ld_bf16 = c.ld_bf16;
   p.rowmap = c.rowmap;
   p.act = c.act;
+  p.trace = nullptr;
 
   CUtensorMap tA0, tA1, tB;
   const uint64_t s = (uint64_t)c.a_stride;
@@ -293,7 +295,11 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   const double bytes = 2.0 * ((double)c.M * c.a_cols / (c.groups > 1 ? 1 : 1) + (double)c.w_rows * p.num_kb * GEMM_BK) +
                        (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
   ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
+  const bool epi_bf16 = c.out_bf16 && !c.out_f32 && !c.resid;
+  if (epi_bf16)
+    gemm_bf16_tcgen05_kernel<BN, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
+  else
+    gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -319,6 +325,7 @@ int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   p.ld_bf16 = c.ld_bf16;
   p.rowmap = c.rowmap;
   p.act = c.act;
+  p.trace = h->gemm_trace;
 
   CUtensorMap tA0, tA1, tB;
   const uint64_t s = (uint64_t)c.a_stride;
@@ -353,7 +360,11 @@ int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel, tA0, tA1, tB, p));
+  const bool epi_bf16 = c.out_bf16 && !c.out_f32 && !c.resid;
+  if (epi_bf16)
+    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<true>, tA0, tA1, tB, p));
+  else
+    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<false>, tA0, tA1, tB, p));
   return 0;
 }
 
@@ -572,6 +583,12 @@ extern "C" int serenc_wavlm_bucket(int delta, int num_buckets, int max_distance)
 extern "C" const char* serenc_last_error(void) { return g_err; }
 extern "C" const char* serenc_version(void) { return "serenc 0.1 (sm_100a; tcgen05 GEMM, mma.sync attention)"; }
 
+extern "C" int serenc_debug_gemm_trace(serenc_handle* h, void* dev_buf) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  h->gemm_trace = reinterpret_cast<long long*>(dev_buf);
+  return 0;
+}
+
 extern "C" int64_t serenc_launch_count(const serenc_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
 
 extern "C" int serenc_set_profiling(serenc_handle* h, int enable) {
@@ -674,9 +691,12 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   }
   if (!st) {
     auto attr = [&](cudaError_t e) { if (e != cudaSuccess && !st) { st = SERENC_ERR_CUDA; serenc::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); } };
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
