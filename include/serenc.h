@@ -68,7 +68,10 @@ typedef struct {
   int32_t n_mels;               /* Whisper: 128                            */
   int32_t max_source_positions; /* Whisper: 1500                           */
   float layer_norm_eps;         /* 1e-5                                    */
-  int32_t reserved[8];
+  int32_t conv_group_norm;      /* W2V: 1 = feat_extract_norm "group" (base checkpoints): GroupNorm on conv0 only */
+  int32_t post_layer_norm;      /* W2V: 1 = do_stable_layer_norm false (base checkpoints): post-LN encoder layers  */
+  int32_t no_feat_proj_ln;      /* W2V: 1 = feature projection without LayerNorm (HuBERT-base)                     */
+  int32_t reserved[5];
 } serenc_config;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------ */

@@ -29,7 +29,8 @@ class SerencConfig(C.Structure):
         ("ffn", C.c_int32), ("conv_dim", C.c_int32), ("conv_bias", C.c_int32), ("wavlm_rel_bias", C.c_int32),
         ("num_buckets", C.c_int32), ("max_distance", C.c_int32), ("pos_conv_kernel", C.c_int32),
         ("pos_conv_groups", C.c_int32), ("n_mels", C.c_int32), ("max_source_positions", C.c_int32),
-        ("layer_norm_eps", C.c_float), ("reserved", C.c_int32 * 8),
+        ("layer_norm_eps", C.c_float), ("conv_group_norm", C.c_int32), ("post_layer_norm", C.c_int32),
+        ("no_feat_proj_ln", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -28,6 +28,7 @@ class EncoderConfig:
     conv_bias: bool = False
     feat_extract_norm: str = "layer"
     do_stable_layer_norm: bool = True
+    feat_proj_layer_norm: bool = True
     num_conv_pos_embeddings: int = 128
     num_conv_pos_embedding_groups: int = 16
     # WavLM
@@ -78,6 +79,20 @@ WAV2VEC2_LARGE_LV60 = _reg(
 HUBERT_LARGE = _reg(
     EncoderConfig("facebook/hubert-large-ll60k", "hubert", 1024, 24, 16, 4096, conv_bias=True),
     "hubert-large-ll60k", "hubert-large")
+# base-size checkpoints: GroupNorm feature encoder, post-LN transformer (benchmark/utils/etc.py:10-15 and
+# configs/old/*wavlmbase* of the reference use them)
+WAVLM_BASE_PLUS = _reg(
+    EncoderConfig("microsoft/wavlm-base-plus", "wavlm", 768, 12, 12, 3072, conv_bias=False, feat_extract_norm="group",
+                  do_stable_layer_norm=False),
+    "microsoft/wavlm-base", "wavlm-base-plus", "wavlm-base")
+WAV2VEC2_BASE = _reg(
+    EncoderConfig("facebook/wav2vec2-base", "wav2vec2", 768, 12, 12, 3072, conv_bias=False, feat_extract_norm="group",
+                  do_stable_layer_norm=False, do_normalize=True, return_attention_mask=False),
+    "facebook/wav2vec2-base-960h", "wav2vec2-base")
+HUBERT_BASE = _reg(
+    EncoderConfig("facebook/hubert-base-ls960", "hubert", 768, 12, 12, 3072, conv_bias=False, feat_extract_norm="group",
+                  do_stable_layer_norm=False, feat_proj_layer_norm=False, do_normalize=False, return_attention_mask=False),
+    "hubert-base-ls960", "hubert-base")
 WHISPER_LARGE_V3 = _reg(
     EncoderConfig("openai/whisper-large-v3", "whisper", 1280, 32, 20, 5120, num_mel_bins=128),
     "whisper-large-v3")
@@ -101,6 +116,13 @@ TINY_HUBERT80 = _reg(  # head_dim 80 and a padded positional-conv group (like Hu
 TINY_W2V120 = _reg(    # head_dim 120 (like XLS-R-2b)
     EncoderConfig("tiny/w2v120", "wav2vec2", 1920, 1, 16, 768, conv_bias=True,
                   num_conv_pos_embeddings=15, num_conv_pos_embedding_groups=16))
+TINY_WAVLM_BASE = _reg(   # GroupNorm conv encoder + post-LN layers + gated bias (like wavlm-base-plus)
+    EncoderConfig("tiny/wavlm-base", "wavlm", 128, 2, 2, 256, conv_bias=False, feat_extract_norm="group",
+                  do_stable_layer_norm=False, num_conv_pos_embeddings=16, num_conv_pos_embedding_groups=4))
+TINY_HUBERT_BASE = _reg(  # no feature-projection LayerNorm, conv bias (exercises the bias + GELU conv epilogue)
+    EncoderConfig("tiny/hubert-base", "hubert", 256, 2, 4, 512, conv_bias=True, feat_extract_norm="group",
+                  do_stable_layer_norm=False, feat_proj_layer_norm=False, num_conv_pos_embeddings=16,
+                  num_conv_pos_embedding_groups=4))
 TINY_WHISPER = _reg(
     EncoderConfig("tiny/whisper", "whisper", 128, 2, 2, 256, num_mel_bins=80))
 TINY_WHISPER128 = _reg(

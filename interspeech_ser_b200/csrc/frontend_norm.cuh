@@ -84,17 +84,26 @@ constexpr int CONV0_TILE = 256;  // frames per block
 
 typedef UttSpan Conv0Utt;
 
-__global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __restrict__ wav,
-                                                                const Conv0Utt* __restrict__ utts,
-                                                                const float2* __restrict__ stats,  // nullptr: already normalised
-                                                                const float* __restrict__ w,       // [512][10]
-                                                                const float* __restrict__ bias,    // [512] or nullptr
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                bf16* __restrict__ out) {
+// MODE 0: LayerNorm over the 512 channels of every frame (feat_extract_norm = "layer").
+// MODE 1: GroupNorm statistics pass (feat_extract_norm = "group", HF WavLMGroupNormConvLayer: per-channel mean /
+//         variance over the utterance's valid frames): writes per-block partial (sum, sum of squares) per channel.
+// MODE 2: GroupNorm apply pass: conv recomputed (10 MACs per output beat a 1 KB round trip), y = gelu(a*scale + shift)
+//         with the per-(utterance, channel) scale/shift produced by conv0_gn_finalize_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__ wav,
+                                                       const Conv0Utt* __restrict__ utts,
+                                                       const float2* __restrict__ stats,  // nullptr: already normalised
+                                                       const float* __restrict__ w,       // [512][10]
+                                                       const float* __restrict__ bias,    // [512] or nullptr
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       bf16* __restrict__ out,
+                                                       double2* __restrict__ gn_partial,      // MODE 1: [B][tiles][512]
+                                                       const float2* __restrict__ gn_affine,  // MODE 2: [B][512] (scale, shift)
+                                                       int tiles_per_utt) {
   // The 160 filter taps of a lane's 16 channels live in REGISTERS for the whole tile, so the inner loop is
   // 160 FFMA + 10 broadcast shared-memory reads per frame (a shared-memory-resident filter made the kernel
   // LDS-bound at ~1 TB/s of output).
-  __shared__ float ws[CONV0_C * CONV0_K];   // staging only: coalesced global read, then per-lane gather
+  __shared__ float ws[8 * CONV0_C * 2];     // filter staging (coalesced global read, per-lane gather); MODE 1 reuses it for the block reduction
   __shared__ float2 s_b[CONV0_C / 2], s_g[CONV0_C / 2], s_be[CONV0_C / 2];
   __shared__ float xs[CONV0_TILE * CONV0_S + CONV0_K];
 
@@ -106,8 +115,14 @@ __global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __re
   for (int i = threadIdx.x; i < CONV0_K * CONV0_C; i += blockDim.x) ws[i] = w[i];
   for (int c = threadIdx.x; c < CONV0_C; c += blockDim.x) {
     reinterpret_cast<float*>(s_b)[c] = bias ? bias[c] : 0.f;
-    reinterpret_cast<float*>(s_g)[c] = gamma[c];
-    reinterpret_cast<float*>(s_be)[c] = beta[c];
+    if (MODE == 0) {
+      reinterpret_cast<float*>(s_g)[c] = gamma[c];
+      reinterpret_cast<float*>(s_be)[c] = beta[c];
+    } else if (MODE == 2) {
+      const float2 a = gn_affine[(int64_t)blockIdx.y * CONV0_C + c];
+      reinterpret_cast<float*>(s_g)[c] = a.x;
+      reinterpret_cast<float*>(s_be)[c] = a.y;
+    }
   }
   float mean = 0.f, rstd = 1.f;
   if (stats) {
@@ -133,12 +148,17 @@ __global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __re
   }
 
   const int t_end = min(CONV0_TILE, u.slot - t0);
+  float gsum[16], gsq[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gsum[i] = gsq[i] = 0.f;
   for (int f = warp; f < t_end; f += 8) {
     const int t = t0 + f;
     uint32_t* orow = reinterpret_cast<uint32_t*>(out + (u.row0 + t) * CONV0_C);
     if (t >= u.T0) {  // slot padding rows: zeros (warp-uniform)
+      if (MODE != 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) orow[32 * i + lane] = 0u;
+        for (int i = 0; i < 8; ++i) orow[32 * i + lane] = 0u;
+      }
       continue;
     }
     float a[16];
@@ -153,6 +173,22 @@ __global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __re
       const float xv = xs[f * CONV0_S + j];
 #pragma unroll
       for (int i = 0; i < 16; ++i) a[i] = fmaf(wr[i][j], xv, a[i]);
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        gsum[i] += a[i];
+        gsq[i] = fmaf(a[i], a[i], gsq[i]);
+      }
+      continue;
+    }
+    if (MODE == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
+        orow[32 * i + lane] = pack_bf16x2(gelu_erf_fast(fmaf(a[2 * i], g.x, be.x)), gelu_erf_fast(fmaf(a[2 * i + 1], g.y, be.y)));
+      }
+      continue;
     }
     float s = 0.f;
 #pragma unroll
@@ -173,6 +209,51 @@ __global__ void __launch_bounds__(256, 1) conv0_ln_gelu_kernel(const float* __re
       orow[32 * i + lane] = pack_bf16x2(y0, y1);
     }
   }
+  if (MODE == 1) {
+    // fixed-order block reduction over the 8 warps (deterministic), in double
+    __syncthreads();                       // xs / ws are dead: reuse ws as the exchange buffer
+    float* ex = ws;                        // [8 warps][512][2]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = 64 * i + 2 * lane;
+      ex[(warp * CONV0_C + c) * 2 + 0] = gsum[2 * i];
+      ex[(warp * CONV0_C + c) * 2 + 1] = gsq[2 * i];
+      ex[(warp * CONV0_C + c + 1) * 2 + 0] = gsum[2 * i + 1];
+      ex[(warp * CONV0_C + c + 1) * 2 + 1] = gsq[2 * i + 1];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < CONV0_C; c += blockDim.x) {
+      double sm = 0.0, sq = 0.0;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) {
+        sm += (double)ex[(wv * CONV0_C + c) * 2 + 0];
+        sq += (double)ex[(wv * CONV0_C + c) * 2 + 1];
+      }
+      gn_partial[((int64_t)blockIdx.y * tiles_per_utt + blockIdx.x) * CONV0_C + c] = make_double2(sm, sq);
+    }
+  }
+}
+
+// per (utterance, channel): mean / biased variance over the valid frames -> scale = gamma * rstd, shift = beta - mean*scale
+__global__ void conv0_gn_finalize_kernel(const double2* __restrict__ partial, const Conv0Utt* __restrict__ utts,
+                                         int tiles_per_utt, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float2* __restrict__ affine) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= CONV0_C) return;
+  const Conv0Utt u = utts[b];
+  const int ntile = (u.T0 + CONV0_TILE - 1) / CONV0_TILE;
+  double sm = 0.0, sq = 0.0;
+  for (int t = 0; t < ntile; ++t) {
+    const double2 p = partial[((int64_t)b * tiles_per_utt + t) * CONV0_C + c];
+    sm += p.x;
+    sq += p.y;
+  }
+  const double n = (double)max(u.T0, 1);
+  const double mean = sm / n;
+  const double var = fmax(sq / n - mean * mean, 0.0);
+  const float scale = gamma[c] * (float)(1.0 / sqrt(var + 1e-5));
+  affine[(int64_t)b * CONV0_C + c] = make_float2(scale, beta[c] - (float)mean * scale);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -219,7 +300,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int64_t rows,
                                                               const int32_t* __restrict__ in_rowmap,
-                                                              const int32_t* __restrict__ out_rowmap, float eps) {
+                                                              const int32_t* __restrict__ out_rowmap, float eps,
+                                                              bf16* __restrict__ out2 = nullptr, int64_t ld_out2 = 0) {
+  // out2: optional second, bf16 copy of the result (post-LN layers: the fp32 residual stream is normalised in place
+  // and the same values feed the next GEMM)
   constexpr int RPW = LnRows<NV>::RPW;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
@@ -275,8 +359,19 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
         o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w);
       }
       store4<TOut>(out + orow[r] * ld_out + c, o);
+      if (out2) store4<bf16>(out2 + orow[r] * ld_out2 + c, o);
     }
   }
+}
+
+// valid rows of the conv6 output (slot layout) -> packed rows, no normalisation (HuBERT-base: feat_proj_layer_norm=False)
+__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, int64_t ld_in, bf16* __restrict__ out, int64_t ld_out,
+                                        int64_t rows, int cols8, const int32_t* __restrict__ in_rowmap) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols8) return;
+  const int64_t r = idx / cols8;
+  const int c = (int)(idx - r * cols8) * 8;
+  *reinterpret_cast<uint4*>(out + r * ld_out + c) = *reinterpret_cast<const uint4*>(in + (int64_t)in_rowmap[r] * ld_in + c);
 }
 
 // ---------------------------------------------------------------------------------------------

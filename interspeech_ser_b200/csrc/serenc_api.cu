@@ -403,7 +403,7 @@ GemmCall linear_call(const bf16* A, int64_t M, int K, const bf16* W, int N) {
 // ---------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut, bool GELU>
 int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64_t ld_out, const float* g, const float* b, int64_t rows,
-                int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st) {
+                int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st, bf16* out2 = nullptr) {
   if (rows <= 0) return 0;
   const int nv = cols / 128;
   const dim3 block(256);
@@ -411,7 +411,7 @@ int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64
 #define SERENC_LN_CASE(NV)                                                                                         \
   case NV:                                                                                                         \
     layernorm_rows_kernel<NV, TIn, TOut, GELU><<<dim3((unsigned)ceil_div64(rows, 8 * LnRows<NV>::RPW)), block, 0, st>>>( \
-        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps);                                                 \
+        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps, out2, (int64_t)cols);                           \
     break;
   switch (nv) {
     SERENC_LN_CASE(1)
@@ -840,11 +840,14 @@ extern "C" int serenc_finalize(serenc_handle* h) {
   if (c.arch == SERENC_ARCH_W2V) {
     for (int i = 0; i < 7; ++i) {
       snprintf(buf, sizeof(buf), "conv%d.weight", i); req.push_back(buf);
-      snprintf(buf, sizeof(buf), "conv%d.ln.weight", i); req.push_back(buf);
-      snprintf(buf, sizeof(buf), "conv%d.ln.bias", i); req.push_back(buf);
+      if (!c.conv_group_norm || i == 0) {
+        snprintf(buf, sizeof(buf), "conv%d.ln.weight", i); req.push_back(buf);
+        snprintf(buf, sizeof(buf), "conv%d.ln.bias", i); req.push_back(buf);
+      }
       if (c.conv_bias) { snprintf(buf, sizeof(buf), "conv%d.bias", i); req.push_back(buf); }
     }
-    for (const char* s : {"featproj.ln.weight", "featproj.ln.bias", "featproj.weight", "featproj.bias", "posconv.weight", "posconv.bias"}) req.push_back(s);
+    for (const char* s : {"featproj.weight", "featproj.bias", "posconv.weight", "posconv.bias"}) req.push_back(s);
+    if (!c.no_feat_proj_ln) { req.push_back("featproj.ln.weight"); req.push_back("featproj.ln.bias"); }
     if (c.wavlm_rel_bias) req.push_back("rel_attn_embed");
   } else {
     for (const char* s : {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "embed_positions", "mel_filters"}) req.push_back(s);
@@ -996,6 +999,55 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
   return 0;
 }
 
+// Post-LN encoder stack (do_stable_layer_norm = false; the base-size checkpoints): encoder LayerNorm BEFORE the
+// layers, each layer  x = LN1(x + attn(x));  x = LN2(x + ffn(x)),  no LayerNorm after the last layer.
+// Wav2Vec2Encoder / Wav2Vec2EncoderLayer, WavLMEncoder / WavLMEncoderLayer (HF modeling_wav2vec2.py:634-713,
+// modeling_wavlm.py:296-337, :375-448).  The LayerNorms run in place on the fp32 stream and also write the bf16
+// copy the next GEMM reads, so the stream is read once per norm.
+int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int tmax, const int32_t* frame_off_dev,
+                      double attn_flops, EmitCtx& e, cudaStream_t st) {
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln)));
+  SERENC_TRY(emit_hidden(h, e, 0, b.x, st));
+  for (int li = 0; li < c.layers; ++li) {
+    const LayerW& l = h->L[li];
+    {
+      GemmCall g = linear_call(b.hln, sumT, d, l.w_qkv, 3 * d);
+      g.bias = l.b_qkv; g.out_bf16 = b.qkv; g.ld_bf16 = 3 * d; g.prof_cls = SERENC_PROF_GEMM_QKV;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    {
+      AttnParams p;
+      p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
+      p.scale = 1.0f / sqrtf((float)h->head_dim);
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
+      SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
+    }
+    {
+      GemmCall g = linear_call(b.att, sumT, d, l.w_o, d);
+      g.bias = l.b_o; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d; g.prof_cls = SERENC_PROF_GEMM_OUT;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln)));
+    {
+      GemmCall g = linear_call(b.hln, sumT, d, l.w_fc1, c.ffn);
+      g.bias = l.b_fc1; g.act = 1; g.out_bf16 = b.ffn; g.ld_bf16 = c.ffn; g.prof_cls = SERENC_PROF_GEMM_FC1;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    {
+      GemmCall g = linear_call(b.ffn, sumT, c.ffn, l.w_fc2, d);
+      g.bias = l.b_fc2; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d; g.prof_cls = SERENC_PROF_GEMM_FC2;
+      SERENC_TRY(launch_gemm(h, g, st));
+    }
+    SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln)));
+    SERENC_TRY(emit_hidden(h, e, li + 1, b.x, st));
+  }
+  if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
+    SERENC_TRY(pool_launch(h, e.acc, sumT, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
+  return 0;
+}
+
 int popcount64(uint64_t v) { int n = 0; while (v) { n += (int)(v & 1); v >>= 1; } return n; }
 
 // ---- wav2vec2-family plan ----
@@ -1047,6 +1099,7 @@ int make_w2v_plan(const serenc_handle* h, const int32_t* len, int batch, W2VPlan
 
 struct W2VWs {
   Conv0Utt* utts; float2* stats; int32_t* foff; int32_t* r6; int32_t *fp_gather, *gap_row, *pos_rowmap;
+  double2* gn_partial; float2* gn_affine; int gn_tiles;
   bf16 *cbuf0, *cbuf1; bf16* featln; bf16* posin;
   StackBufs sb; float* acc;
   size_t bytes;
@@ -1063,6 +1116,14 @@ void carve_w2v(const serenc_handle* h, const W2VPlan& p, void* base, W2VWs* w) {
   w->fp_gather = cv.take<int32_t>(p.sumT);
   w->gap_row = cv.take<int32_t>(p.sumT);
   w->pos_rowmap = cv.take<int32_t>(p.mpos);
+  w->gn_tiles = 0; w->gn_partial = nullptr; w->gn_affine = nullptr;
+  if (c.conv_group_norm) {
+    int slot_max = 0;
+    for (int b = 0; b < p.batch; ++b) slot_max = slot_max > ((p.T[6][b] + 2) << 6) ? slot_max : ((p.T[6][b] + 2) << 6);
+    w->gn_tiles = ceil_div(slot_max, CONV0_TILE);
+    w->gn_partial = cv.take<double2>((size_t)p.batch * w->gn_tiles * CONV0_C);
+    w->gn_affine = cv.take<float2>((size_t)p.batch * CONV0_C);
+  }
   w->cbuf0 = cv.take<bf16>((size_t)p.rows[0] * C);  // conv0, conv2, conv4, conv6 outputs
   w->cbuf1 = cv.take<bf16>((size_t)p.rows[1] * C);  // conv1, conv3, conv5 outputs
   w->featln = cv.take<bf16>((size_t)p.sumT * C);
@@ -1216,10 +1277,22 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     const dim3 grid(ceil_div(slot_max, CONV0_TILE), batch);
     double t0sum = 0, nsamp0 = 0;
     for (int b = 0; b < batch; ++b) { t0sum += p.T[0][b]; nsamp0 += sample_len[b]; }
-    ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, 4.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
-    conv0_ln_gelu_kernel<<<grid, 256, 0, st>>>(wav_dev, w.utts, normalize ? w.stats : nullptr, h->conv0_w,
-                                               c.conv_bias ? h->conv_b[0] : nullptr, h->conv_g[0], h->conv_be[0], w.cbuf0);
-    SERENC_CUDA_OK(cudaGetLastError());
+    const float2* stp = normalize ? w.stats : nullptr;
+    const float* b0 = c.conv_bias ? h->conv_b[0] : nullptr;
+    if (!c.conv_group_norm) {
+      ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, 4.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
+      conv0_kernel<0><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, h->conv_g[0], h->conv_be[0], w.cbuf0, nullptr, nullptr, 0);
+      SERENC_CUDA_OK(cudaGetLastError());
+    } else {
+      // GroupNorm(512 groups) on conv0: statistics over each utterance's valid frames, then recompute + apply
+      ProfScope ps(h, SERENC_PROF_CONV0, 3, 4.0 * t0sum * CONV0_C * CONV0_K, 8.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
+      conv0_kernel<1><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, w.gn_partial, nullptr, w.gn_tiles);
+      SERENC_CUDA_OK(cudaGetLastError());
+      conv0_gn_finalize_kernel<<<dim3(CONV0_C / 128, batch), 128, 0, st>>>(w.gn_partial, w.utts, w.gn_tiles, h->conv_g[0], h->conv_be[0], w.gn_affine);
+      SERENC_CUDA_OK(cudaGetLastError());
+      conv0_kernel<2><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, nullptr, w.gn_affine, w.gn_tiles);
+      SERENC_CUDA_OK(cudaGetLastError());
+    }
   }
   bf16* cin = w.cbuf0;
   bf16* cout = w.cbuf1;
@@ -1230,13 +1303,22 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     g.bias = c.conv_bias ? h->conv_b[k] : nullptr;
     g.out_bf16 = cout; g.ld_bf16 = C;
     g.prof_cls = SERENC_PROF_GEMM_CONV;
+    g.act = c.conv_group_norm ? 1 : 0;   // "group" encoders: conv -> GELU (no norm after layer 0), fused in the epilogue
     { double tk = 0; for (int b = 0; b < batch; ++b) tk += p.T[k][b]; g.alg_flops = 2.0 * tk * C * C * W2V_K[k]; }
     SERENC_TRY(launch_gemm(h, g, st));
-    SERENC_TRY((launch_ln_t<bf16, bf16, true>(h, cout, C, cout, C, h->conv_g[k], h->conv_be[k], p.rows[k], C, nullptr, nullptr, 1e-5f, st)));
+    if (!c.conv_group_norm)
+      SERENC_TRY((launch_ln_t<bf16, bf16, true>(h, cout, C, cout, C, h->conv_g[k], h->conv_be[k], p.rows[k], C, nullptr, nullptr, 1e-5f, st)));
     bf16* t = cin; cin = cout; cout = t;
   }
   // ---- feature projection: LN(512) over the valid frames (gathered into the packed layout) -> Linear(512 -> d) ----
-  SERENC_TRY((launch_ln_t<bf16, bf16, false>(h, cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
+  if (!c.no_feat_proj_ln) {
+    SERENC_TRY((launch_ln_t<bf16, bf16, false>(h, cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
+  } else {
+    ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, (double)p.sumT * C * 4, st);
+    const int64_t nthr = p.sumT * (C / 8);
+    gather_rows_bf16_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(cin, C, w.featln, C, p.sumT, C / 8, w.fp_gather);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
   {
     GemmCall g = linear_call(w.featln, p.sumT, C, h->fp_w, d);
     g.bias = h->fp_b; g.out_f32 = w.sb.x; g.ld_f32 = d;
@@ -1269,7 +1351,8 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   e.sumT = p.sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = nullptr;
   double attn_flops = 0.0;
   for (int b = 0; b < batch; ++b) attn_flops += 4.0 * (double)p.T[6][b] * p.T[6][b] * d;
-  SERENC_TRY(run_stack(h, w.sb, p.sumT, batch, p.tmax, w.foff, attn_flops, e, st));
+  if (c.post_layer_norm) SERENC_TRY(run_stack_post_ln(h, w.sb, p.sumT, batch, p.tmax, w.foff, attn_flops, e, st));
+  else SERENC_TRY(run_stack(h, w.sb, p.sumT, batch, p.tmax, w.foff, attn_flops, e, st));
   return 0;
 }
 

@@ -60,10 +60,12 @@ class Engine:
         c.pos_conv_kernel, c.pos_conv_groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
         c.n_mels, c.max_source_positions = cfg.num_mel_bins, cfg.max_source_positions
         c.layer_norm_eps = cfg.layer_norm_eps
+        c.conv_group_norm = int(cfg.feat_extract_norm == "group")
+        c.post_layer_norm = int(not cfg.do_stable_layer_norm)
+        c.no_feat_proj_ln = int(not cfg.feat_proj_layer_norm)
         if cfg.arch == ARCH_W2V:
-            if cfg.feat_extract_norm != "layer" or not cfg.do_stable_layer_norm:
-                raise NotImplementedError("only feat_extract_norm='layer' + do_stable_layer_norm=True encoders "
-                                          "(the *-large / xlarge / xls-r checkpoints the reference uses) are built")
+            if cfg.feat_extract_norm not in ("layer", "group"):
+                raise ValueError(f"feat_extract_norm={cfg.feat_extract_norm!r} has to be 'layer' or 'group'")
             if tuple(cfg.conv_kernel) != (10, 3, 3, 3, 3, 2, 2) or tuple(cfg.conv_stride) != (5, 2, 2, 2, 2, 2, 2):
                 raise NotImplementedError("unsupported feature-encoder geometry")
         h = C.c_void_p()

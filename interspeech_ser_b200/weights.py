@@ -122,10 +122,12 @@ def from_hf_state_dict(cfg: EncoderConfig, sd: Mapping[str, object]) -> Dict[str
         out[f"conv{i}.weight"] = _np(sd[b + "conv.weight"])
         if cfg.conv_bias:
             out[f"conv{i}.bias"] = _np(sd[b + "conv.bias"])
-        out[f"conv{i}.ln.weight"] = _np(sd[b + "layer_norm.weight"])
-        out[f"conv{i}.ln.bias"] = _np(sd[b + "layer_norm.bias"])
-    out["featproj.ln.weight"] = _np(sd["feature_projection.layer_norm.weight"])
-    out["featproj.ln.bias"] = _np(sd["feature_projection.layer_norm.bias"])
+        if cfg.feat_extract_norm == "layer" or i == 0:   # 'group': only layer 0 carries a (Group)Norm
+            out[f"conv{i}.ln.weight"] = _np(sd[b + "layer_norm.weight"])
+            out[f"conv{i}.ln.bias"] = _np(sd[b + "layer_norm.bias"])
+    if cfg.feat_proj_layer_norm:
+        out["featproj.ln.weight"] = _np(sd["feature_projection.layer_norm.weight"])
+        out["featproj.ln.bias"] = _np(sd["feature_projection.layer_norm.bias"])
     out["featproj.weight"] = _np(sd["feature_projection.projection.weight"])
     out["featproj.bias"] = _np(sd["feature_projection.projection.bias"])
     pc = "encoder.pos_conv_embed.conv."
@@ -208,8 +210,10 @@ def random_init(cfg: EncoderConfig, seed: int = 0) -> Dict[str, np.ndarray]:
         out[f"conv{i}.weight"] = normal((C, cin, k), math.sqrt(2.0 / (cin * k)))
         if cfg.conv_bias:
             out[f"conv{i}.bias"] = normal((C,), 0.05)
-        out[f"conv{i}.ln.weight"], out[f"conv{i}.ln.bias"] = ln(C)
-    out["featproj.ln.weight"], out["featproj.ln.bias"] = ln(C)
+        if cfg.feat_extract_norm == "layer" or i == 0:
+            out[f"conv{i}.ln.weight"], out[f"conv{i}.ln.bias"] = ln(C)
+    if cfg.feat_proj_layer_norm:
+        out["featproj.ln.weight"], out["featproj.ln.bias"] = ln(C)
     out["featproj.weight"] = normal((d, C), 1.0 / math.sqrt(C))
     out["featproj.bias"] = normal((d,), 0.02)
     kpos, g = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups

@@ -75,7 +75,8 @@ def hf_model(cfg: C.EncoderConfig, w):
     common = dict(hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
                   num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
                   conv_dim=list(cfg.conv_dim), conv_kernel=list(cfg.conv_kernel), conv_stride=list(cfg.conv_stride),
-                  conv_bias=cfg.conv_bias, feat_extract_norm="layer", do_stable_layer_norm=True,
+                  conv_bias=cfg.conv_bias, feat_extract_norm=cfg.feat_extract_norm,
+                  do_stable_layer_norm=cfg.do_stable_layer_norm,
                   num_conv_pos_embeddings=cfg.num_conv_pos_embeddings,
                   num_conv_pos_embedding_groups=cfg.num_conv_pos_embedding_groups, hidden_dropout=0.0,
                   attention_dropout=0.0, activation_dropout=0.0, feat_proj_dropout=0.0, layerdrop=0.0,
@@ -83,7 +84,7 @@ def hf_model(cfg: C.EncoderConfig, w):
     if cfg.family == "wavlm":
         m = tr.WavLMModel(tr.WavLMConfig(num_buckets=cfg.num_buckets, max_bucket_distance=cfg.max_bucket_distance, **common))
     elif cfg.family == "hubert":
-        m = tr.HubertModel(tr.HubertConfig(feat_proj_layer_norm=True, **common))
+        m = tr.HubertModel(tr.HubertConfig(feat_proj_layer_norm=cfg.feat_proj_layer_norm, **common))
     else:
         m = tr.Wav2Vec2Model(tr.Wav2Vec2Config(**common))
     m = m.eval()
@@ -92,8 +93,10 @@ def hf_model(cfg: C.EncoderConfig, w):
         sd[b + "conv.weight"] = t(w[f"conv{i}.weight"])
         if cfg.conv_bias:
             sd[b + "conv.bias"] = t(w[f"conv{i}.bias"])
-        sd[b + "layer_norm.weight"], sd[b + "layer_norm.bias"] = t(w[f"conv{i}.ln.weight"]), t(w[f"conv{i}.ln.bias"])
-    sd["feature_projection.layer_norm.weight"], sd["feature_projection.layer_norm.bias"] = t(w["featproj.ln.weight"]), t(w["featproj.ln.bias"])
+        if cfg.feat_extract_norm == "layer" or i == 0:
+            sd[b + "layer_norm.weight"], sd[b + "layer_norm.bias"] = t(w[f"conv{i}.ln.weight"]), t(w[f"conv{i}.ln.bias"])
+    if cfg.feat_proj_layer_norm:
+        sd["feature_projection.layer_norm.weight"], sd["feature_projection.layer_norm.bias"] = t(w["featproj.ln.weight"]), t(w["featproj.ln.bias"])
     sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"] = t(w["featproj.weight"]), t(w["featproj.bias"])
     pw = t(w["posconv.weight"])
     # weight_norm(dim=2): choose g = ||W[:, :, k]|| and v = W so that g * v / ||v|| == W
@@ -267,7 +270,7 @@ def main():
         golden_buckets()
         golden_logmel_signals()
     tiny_lengths = [400, 401, 719, 720, 4001, 17777, 32000]
-    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120"):
+    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120", "tiny/wavlm-base", "tiny/hubert-base"):
         if want(name):
             golden_w2v(name, tiny_lengths)
     for name in ("tiny/whisper", "tiny/whisper128"):

@@ -59,23 +59,32 @@ def w2v_num_frames(n: int, kernels=(10, 3, 3, 3, 3, 2, 2), strides=(5, 2, 2, 2, 
 # wav2vec2 / HuBERT / WavLM
 # --------------------------------------------------------------------------------------------------
 def conv_feature_encoder(cfg, w: W, x: torch.Tensor) -> torch.Tensor:
-    """7 x (Conv1d -> LayerNorm over channels -> exact GELU), feat_extract_norm='layer'
+    """feat_extract_norm='layer' (large / xlarge checkpoints): 7 x (Conv1d -> LayerNorm over channels -> exact GELU)
     (WavLMLayerNormConvLayer, HF modeling_wavlm.py:703-727; WavLMFeatureEncoder.forward :775-789).
-    x: [L] normalised samples -> [T, 512]."""
+    feat_extract_norm='group' (base checkpoints): layer 0 = Conv1d -> GroupNorm(groups = channels), i.e. per-channel
+    statistics over TIME -> GELU (WavLMGroupNormConvLayer :730-751); layers 1-6 = Conv1d -> GELU
+    (WavLMNoLayerNormConvLayer :682-700).  x: [L] normalised samples -> [T, 512]."""
     h = x[None, None, :]
     for i in range(7):
         b = _t(w[f"conv{i}.bias"]) if cfg.conv_bias else None
         h = F.conv1d(h, _t(w[f"conv{i}.weight"]), b, stride=cfg.conv_stride[i])
-        h = h.transpose(-2, -1)
-        h = F.layer_norm(h, (h.shape[-1],), _t(w[f"conv{i}.ln.weight"]), _t(w[f"conv{i}.ln.bias"]), 1e-5)
-        h = h.transpose(-2, -1)
+        if cfg.feat_extract_norm == "layer":
+            h = h.transpose(-2, -1)
+            h = F.layer_norm(h, (h.shape[-1],), _t(w[f"conv{i}.ln.weight"]), _t(w[f"conv{i}.ln.bias"]), 1e-5)
+            h = h.transpose(-2, -1)
+        elif i == 0:
+            C = h.shape[1]
+            h = F.group_norm(h, C, _t(w["conv0.ln.weight"]), _t(w["conv0.ln.bias"]), 1e-5)
         h = F.gelu(h)
     return h[0].transpose(0, 1).contiguous()
 
 
 def feature_projection(cfg, w: W, feats: torch.Tensor) -> torch.Tensor:
-    """LayerNorm(512) -> Linear(512 -> d) (WavLMFeatureProjection, HF modeling_wavlm.py:93-105)."""
-    h = F.layer_norm(feats, (feats.shape[-1],), _t(w["featproj.ln.weight"]), _t(w["featproj.ln.bias"]), cfg.layer_norm_eps)
+    """LayerNorm(512) -> Linear(512 -> d) (WavLMFeatureProjection, HF modeling_wavlm.py:93-105); HuBERT-base skips
+    the LayerNorm (`feat_proj_layer_norm=False`, HF models/hubert/modular_hubert.py:98-113)."""
+    h = feats
+    if getattr(cfg, "feat_proj_layer_norm", True):
+        h = F.layer_norm(h, (h.shape[-1],), _t(w["featproj.ln.weight"]), _t(w["featproj.ln.bias"]), cfg.layer_norm_eps)
     return F.linear(h, _t(w["featproj.weight"]), _t(w["featproj.bias"]))
 
 
@@ -158,6 +167,29 @@ def encoder_layer(cfg, w: W, li: int, x: torch.Tensor, bias, whisper: bool = Fal
     return x + F.linear(h, _t(w[f"layer{li}.fc2.weight"]), _t(w[f"layer{li}.fc2.bias"]))
 
 
+def encoder_layer_post_ln(cfg, w: W, li: int, x: torch.Tensor, bias) -> torch.Tensor:
+    """Post-LN block of the base-size checkpoints (WavLMEncoderLayer, HF modeling_wavlm.py:298-336; Wav2Vec2EncoderLayer,
+    modeling_wav2vec2.py:576-609):  x = LN1(x + Attn(x));  x = LN2(x + FFN(x))."""
+    d = x.shape[-1]
+    x = x + self_attention(cfg, w, li, x, bias)
+    x = F.layer_norm(x, (d,), _t(w[f"layer{li}.ln1.weight"]), _t(w[f"layer{li}.ln1.bias"]), cfg.layer_norm_eps)
+    h = F.gelu(F.linear(x, _t(w[f"layer{li}.fc1.weight"]), _t(w[f"layer{li}.fc1.bias"])))
+    x = x + F.linear(h, _t(w[f"layer{li}.fc2.weight"]), _t(w[f"layer{li}.fc2.bias"]))
+    return F.layer_norm(x, (d,), _t(w[f"layer{li}.ln2.weight"]), _t(w[f"layer{li}.ln2.bias"]), cfg.layer_norm_eps)
+
+
+def run_stack_post_ln(cfg, w: W, x: torch.Tensor, bias) -> List[torch.Tensor]:
+    """WavLMEncoder / Wav2Vec2Encoder (do_stable_layer_norm=False; HF modeling_wavlm.py:376-447): the encoder LayerNorm
+    comes right after the positional conv, [0] = its output, [i] = output of layer i (already normalised)."""
+    d = x.shape[-1]
+    x = F.layer_norm(x, (d,), _t(w["final_ln.weight"]), _t(w["final_ln.bias"]), cfg.layer_norm_eps)
+    hs = [x]
+    for li in range(cfg.num_hidden_layers):
+        x = encoder_layer_post_ln(cfg, w, li, x, bias)
+        hs.append(x)
+    return hs
+
+
 def run_stack(cfg, w: W, x: torch.Tensor, bias, whisper: bool = False) -> List[torch.Tensor]:
     """Encoder loop + final LayerNorm; returns the HF `hidden_states` tuple: L+1 tensors, [0] = stack input,
     [i] = residual stream after layer i, [L] = after the final LayerNorm
@@ -182,6 +214,8 @@ def w2v_hidden_states(cfg, w: W, wav: np.ndarray, normalize: bool = True) -> Lis
     h = feature_projection(cfg, w, feats)
     h = h + pos_conv_embed(cfg, w, h)
     bias = wavlm_position_bias(cfg, w, h.shape[0]) if cfg.family == "wavlm" else None
+    if not cfg.do_stable_layer_norm:
+        return run_stack_post_ln(cfg, w, h, bias)
     return run_stack(cfg, w, h, bias)
 
 

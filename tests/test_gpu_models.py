@@ -59,7 +59,7 @@ def load_golden(golden_dir, name):
 # ------------------------------------------------------------------------------------------------
 # wav2vec2 / HuBERT / WavLM
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120"])
+@pytest.mark.parametrize("name", ["tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120", "tiny/wavlm-base", "tiny/hubert-base"])
 def test_w2v_every_hidden_state_vs_oracle_and_hf_golden(golden_dir, name):
     """Ragged batch incl. the edge lengths 400 / 401 / 719 / 720 (1, 1, 1, 2 frames): every hidden-state index, so
     both readings of the reference's layer-index defect are pinned."""

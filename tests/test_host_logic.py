@@ -58,7 +58,7 @@ def test_hf_state_dict_conversion_roundtrip():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     pytest.importorskip("transformers")
     from oracle.make_golden import hf_model
-    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/whisper"):
+    for name in ("tiny/wavlm", "tiny/wav2vec2", "tiny/whisper", "tiny/wavlm-base", "tiny/hubert-base"):
         cfg = configs.get_config(name)
         w = random_init(cfg, 1)
         back = from_hf_state_dict(cfg, hf_model(cfg, w).state_dict())

@@ -26,7 +26,7 @@ def load(golden_dir, name):
     return np.load(path)
 
 
-@pytest.mark.parametrize("name", ["tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120"])
+@pytest.mark.parametrize("name", ["tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120", "tiny/wavlm-base", "tiny/hubert-base"])
 def test_w2v_oracle_matches_hf_golden(golden_dir, name):
     g = load(golden_dir, name)
     cfg = configs.get_config(name)
