@@ -36,6 +36,9 @@ def build_parser(whisper: bool) -> argparse.ArgumentParser:
     p.add_argument("--frame_budget", type=int, default=28416, help="max frames per packed batch (111 x 256: whole GEMM waves)")
     p.add_argument("--skip_existing", action="store_true", help="resume: skip files whose .pt already exists")
     p.add_argument("--pooled_path", type=str, default="", help="also save masked-mean pooled embeddings {names, embeddings[N, D]}")
+    p.add_argument("--checkpoint", type=str, default="",
+                   help="weights file/dir for --ssl_type's architecture; a peft LoRA classifier state dict "
+                        "(preprocess_speech_pretrained.py:173) is merged into dense weights at load")
     if not whisper:
         p.add_argument("--compat_layer_from_dir_count", action="store_true",
                        help="literal preprocess_speech.py:41,67 behaviour: index hidden_states by the number of files already in --save_path")
@@ -82,7 +85,10 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
 
     print(f"Extracting features using {args.ssl_type}")
     try:
-        model = AutoModel.from_pretrained(args.ssl_type, device=local_rank, random_init=args.random_init or None, seed=0)
+        if args.checkpoint:
+            model = AutoModel.from_pretrained(args.checkpoint, device=local_rank, config_name=args.ssl_type)
+        else:
+            model = AutoModel.from_pretrained(args.ssl_type, device=local_rank, random_init=args.random_init or None, seed=0)
     except OSError:
         print(f"Error: No pretrained model found with the name {args.ssl_type}")
         print("Something went wrong, make sure everything is correct before running again!")

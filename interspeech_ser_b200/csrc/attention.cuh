@@ -36,6 +36,7 @@ struct AttnParams {
   const float* gru_b;     // [8]
   const float* gru_const; // [H]
   const float* btab;      // [H, 2*WAVLM_MAXD-1]
+  long long* trace = nullptr;  // debug (serenc_debug_gemm_trace): per-CTA clock stamps of the tcgen05 kernel
 };
 
 template <int HD>

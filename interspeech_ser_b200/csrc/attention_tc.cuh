@@ -13,9 +13,10 @@
 //
 // Keys are processed 64 at a time. TMEM: S = columns [0, 64), O = columns [64, 128) of a 128-column allocation;
 // shared memory Q 16 KB + K 8 KB + V 8 KB + P 16 KB, single-buffered (K_{j+1} is fetched as soon as S_j is
-// complete, V_{j+1} as soon as O += P_j V_j is). The phases of one CTA are serial; FOUR CTAs per SM (<= 80
-// registers: the softmax makes two passes over S in TMEM instead of holding the row) overlap one CTA's softmax
-// with the others' MMAs and loads.
+// complete, V_{j+1} as soon as O += P_j V_j is). S_{j+1} = Q K_{j+1}^T is issued the moment the softmax threads
+// have finished reading S_j, AHEAD of O += P_j V_j, so that MMA and its commit latency sit under the next row-max
+// pass. FOUR CTAs per SM (<= 80 registers: the softmax makes two passes over S in TMEM instead of holding the
+// row) overlap one CTA's softmax with the others' MMAs and loads.
 // V is consumed as an MN-major (head-dim contiguous) B operand directly from its row-major [key, d] tile.
 #pragma once
 #include "attention.cuh"
@@ -31,7 +32,8 @@ constexpr int FA_Q_BYTES = FA_BM * FA_HD * 2;   // 16 KB
 constexpr int FA_KV_BYTES = FA_BN * FA_HD * 2;  // 8 KB
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;   // 16 KB
 constexpr int FA_WIN = FA_BM + FA_BN - 1;       // bias window entries per (q tile, key block)
-constexpr int FA_SMEM_BYTES = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + 8 * FA_HD * 4 /*gate weights*/ +
+constexpr int FA_GW_BYTES = 2 * FA_HD * 4;      // gate weights, pre-summed over the two groups of four outputs
+constexpr int FA_SMEM_BYTES = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + FA_GW_BYTES +
                               2 * 192 * 4 /*bias windows*/ + 64 /*barriers*/ + 1024;
 constexpr int FA_TMEM_COLS = 128;
 constexpr uint32_t FA_WAIT_HINT_NS = 2000;   // softmax threads sleep (NANOSLEEP.SYNCS) instead of spinning on S / O barriers
@@ -62,6 +64,12 @@ __device__ __forceinline__ void softmax_group_sync() {  // the 128 softmax threa
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+constexpr int FA_TRACE_SLOTS = 48;   // [0,24): softmax thread 0, [24,48): control thread
+constexpr int FA_TRACE_CTAS = 64;    // CTAs [0,32) and [2048,2080) of the linearised grid
+__device__ __forceinline__ void fa_stamp(long long* tr, int slot) {
+  if (tr) tr[slot] = clock64();
+}
+
 template <bool WAVLM>
 __global__ void __launch_bounds__(FA_THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
@@ -71,9 +79,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + FA_Q_BYTES;
   uint8_t* sV = sK + FA_KV_BYTES;
   uint8_t* sP = sV + FA_KV_BYTES;
-  float4* s_gw = reinterpret_cast<float4*>(sP + FA_P_BYTES);  // [k][8 outputs]
-  float* s_win = reinterpret_cast<float*>(sP + FA_P_BYTES + 8 * FA_HD * 4);  // [2][192]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES + 8 * FA_HD * 4 + 2 * 192 * 4);
+  float4* s_gw = reinterpret_cast<float4*>(sP + FA_P_BYTES);  // [k / 2] = (wa[k], wb[k], wa[k+1], wb[k+1])
+  float* s_win = reinterpret_cast<float*>(sP + FA_P_BYTES + FA_GW_BYTES);  // [2][192]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES + FA_GW_BYTES + 2 * 192 * 4);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;
   uint64_t* bar_v = bars + 2;
@@ -89,6 +97,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (i0 >= T) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkv = (T + FA_BN - 1) / FA_BN;
+  long long* tr = nullptr;
+  if (p.trace && (tid == 0 || tid == 128)) {
+    const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int idx = lin < 32 ? lin : (lin >= 2048 && lin < 2080 ? lin - 2048 + 32 : -1);
+    if (idx >= 0) tr = p.trace + (int64_t)idx * FA_TRACE_SLOTS + (tid == 128 ? 24 : 0);
+  }
+  fa_stamp(tr, 0);
 
   if (warp == 4) {
     if (lane == 0) {
@@ -106,17 +121,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_alloc(tmem_slot, FA_TMEM_COLS);
     tmem_relinquish();
   }
-  if (WAVLM) {
-    float* gw = reinterpret_cast<float*>(s_gw);
-    for (int i = tid; i < 8 * FA_HD; i += FA_THREADS) {
-      const int o = i / FA_HD, k = i - o * FA_HD;
-      gw[k * 8 + o] = __ldg(p.gru_w + i);
-    }
+  if (WAVLM && tid < 2 * FA_HD) {
+    // the gate only needs the SUMS of outputs 0-3 and 4-7 of gru_rel_pos_linear (HF modeling_wavlm.py:170-172:
+    // view(.., 2, 4).sum(-1)), so the [8, 64] weight collapses to two 64-vectors
+    const int k = tid >> 1, g = tid & 1;
+    const float* w = p.gru_w + g * 4 * FA_HD + k;
+    reinterpret_cast<float*>(s_gw)[tid] = (__ldg(w) + __ldg(w + FA_HD)) + (__ldg(w + 2 * FA_HD) + __ldg(w + 3 * FA_HD));
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  fa_stamp(tr, 1);
 
   if (warp == 4) {
     // ------------------------------ control: TMA + MMA issue ------------------------------
@@ -130,40 +146,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_2d(sV, &tmKV, bar_v, colv, r0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);                 // Q K^T: both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(FA_BM, FA_HD) | (1u << 16);    // P V: B (= V) MN-major
+      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t kdesc = umma_desc_sw128(smem_u32(sK));
+      const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
       mbar_wait(bar_q, 0);
+      fa_stamp(tr, 2);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < FA_HD / 16; ++k)
+        umma_bf16_ss(tmem_base + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+      umma_commit(bar_s);
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = (uint32_t)(j & 1);
-        mbar_wait(bar_k, ph);
-        tc_fence_after();
-        {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sQ));
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sK));
-#pragma unroll
-          for (int k = 0; k < FA_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + FA_TMEM_S, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-          umma_commit(bar_s);
-        }
-        mbar_wait(bar_s, ph);  // S complete => K tile free
-        if (j + 1 < nkv) {
+        const bool more = j + 1 < nkv;
+        mbar_wait(bar_s, ph);  // S_j complete => K tile free
+        if (j < 4) fa_stamp(tr, 4 + 4 * j);
+        if (more) {
           mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
           tma_load_2d(sK, &tmKV, bar_k, colk, r0 + (j + 1) * FA_BN);
         }
-        mbar_wait(bar_p, ph);  // P_j in shared memory, O rescaled
+        mbar_wait(bar_p, ph);  // P_j in shared memory, every softmax thread is done reading S_j, O rescaled
+        if (j < 4) fa_stamp(tr, 5 + 4 * j);
         tc_fence_after();
-        mbar_wait(bar_v, ph);
-        tc_fence_after();
-        {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sP));
+        if (more) {
+          // S_{j+1} goes to the tensor core AHEAD of O += P_j V_j: the softmax of block j+1 (its row-max pass only
+          // needs S) starts as soon as possible, and P_j V_j completes underneath it.
+          mbar_wait(bar_k, ph ^ 1u);
+          tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < FA_BN / 16; ++k) {
-            // A = P: +32 B per 16 keys inside the swizzle row; B = V (MN-major): 16 keys = 16 rows of 128 B
-            const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + k * 16 * 128));
-            umma_bf16_ss(tmem_base + FA_TMEM_O, adesc + (uint64_t)(2 * k), bdesc, idesc_o, (uint32_t)((j | k) != 0));
-          }
-          umma_commit(bar_o);
+          for (int k = 0; k < FA_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+          umma_commit(bar_s);
         }
-        mbar_wait(bar_o, ph);  // O += P V complete => V tile and P free
-        if (j + 1 < nkv) {
+        mbar_wait(bar_v, ph);
+        if (j < 4) fa_stamp(tr, 6 + 4 * j);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < FA_BN / 16; ++k) {
+          // A = P: +32 B per 16 keys inside the swizzle row; B = V (MN-major): 16 keys = 16 rows of 128 B
+          const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + k * 16 * 128));
+          umma_bf16_ss(tmem_base + FA_TMEM_O, pdesc + (uint64_t)(2 * k), bdesc, idesc_o, (uint32_t)((j | k) != 0));
+        }
+        umma_commit(bar_o);
+        if (more) {
+          mbar_wait(bar_o, ph);  // O += P_j V_j complete => V tile free
+          if (j < 4) fa_stamp(tr, 7 + 4 * j);
           mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
           tma_load_2d(sV, &tmKV, bar_v, colv, r0 + (j + 1) * FA_BN);
         }
@@ -183,40 +211,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (WAVLM && row_valid) {
       // gate (HF modeling_wavlm.py:167-176) from the layer input row of this head
       const uint4* x4 = reinterpret_cast<const uint4*>(p.hln + (int64_t)(r0 + qi) * p.d + h * FA_HD);
-      float acc[8];
+      float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = 0.f;
-#pragma unroll 2
       for (int c = 0; c < FA_HD / 8; ++c) {
         const uint4 u = __ldg(x4 + c);
         const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 xv = unpack_bf16x2(uu[e]);
-          const int k = c * 8 + e * 2;
-          const float4 w0 = s_gw[k * 2], w1 = s_gw[k * 2 + 1], w2 = s_gw[k * 2 + 2], w3 = s_gw[k * 2 + 3];
-          acc[0] = fmaf(xv.x, w0.x, acc[0]); acc[1] = fmaf(xv.x, w0.y, acc[1]);
-          acc[2] = fmaf(xv.x, w0.z, acc[2]); acc[3] = fmaf(xv.x, w0.w, acc[3]);
-          acc[4] = fmaf(xv.x, w1.x, acc[4]); acc[5] = fmaf(xv.x, w1.y, acc[5]);
-          acc[6] = fmaf(xv.x, w1.z, acc[6]); acc[7] = fmaf(xv.x, w1.w, acc[7]);
-          acc[0] = fmaf(xv.y, w2.x, acc[0]); acc[1] = fmaf(xv.y, w2.y, acc[1]);
-          acc[2] = fmaf(xv.y, w2.z, acc[2]); acc[3] = fmaf(xv.y, w2.w, acc[3]);
-          acc[4] = fmaf(xv.y, w3.x, acc[4]); acc[5] = fmaf(xv.y, w3.y, acc[5]);
-          acc[6] = fmaf(xv.y, w3.z, acc[6]); acc[7] = fmaf(xv.y, w3.w, acc[7]);
+          const float4 w = s_gw[c * 4 + e];
+          a0 = fmaf(xv.x, w.x, a0); b0 = fmaf(xv.x, w.y, b0);
+          a1 = fmaf(xv.y, w.z, a1); b1 = fmaf(xv.y, w.w, b1);
         }
       }
-      float sa = 0.f, sb = 0.f;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        sa += acc[o] + __ldg(p.gru_b + o);
-        sb += acc[o + 4] + __ldg(p.gru_b + o + 4);
-      }
+      const float sa = (a0 + a1) + ((__ldg(p.gru_b + 0) + __ldg(p.gru_b + 1)) + (__ldg(p.gru_b + 2) + __ldg(p.gru_b + 3)));
+      const float sb = (b0 + b1) + ((__ldg(p.gru_b + 4) + __ldg(p.gru_b + 5)) + (__ldg(p.gru_b + 6) + __ldg(p.gru_b + 7)));
       const float ga = 1.f / (1.f + __expf(-sa));
       const float gb = 1.f / (1.f + __expf(-sb));
       gate = (ga * (gb * __ldg(p.gru_const + h) - 1.f) + 2.f) * LOG2E;
     }
     const float* btab_h = WAVLM ? p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1) : nullptr;
 
+    fa_stamp(tr, 2);
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = (uint32_t)(j & 1);
@@ -234,6 +250,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         softmax_group_sync();
       }
       mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_s, ph);
+      if (j < 4) fa_stamp(tr, 4 + 4 * j);
       tc_fence_after();
 
       // pass 1: row maximum of  x = s * scale * log2e (+ gate * bias). Without bias the maximum is taken on the
@@ -268,6 +285,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (!WAVLM) mx *= sc2;
       }
+      if (j < 4) fa_stamp(tr, 5 + 4 * j);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
 
@@ -288,6 +306,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
 
+      if (j < 4) fa_stamp(tr, 6 + 4 * j);
       // pass 2: p = exp2(x - m), row sum, P (bf16) -> shared memory (K-major SW128: chunk = key / 8, XOR row % 8)
       float rs = 0.f;
       if (warp_valid) {
@@ -334,10 +353,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       fence_proxy_async_smem();   // generic-proxy writes of P -> visible to the tensor core's async proxy
       tc_fence_before();
       mbar_arrive(bar_p);
+      if (j < 4) fa_stamp(tr, 7 + 4 * j);
     }
 
     // ------------------------------ epilogue: O / l -> bf16 ------------------------------
     mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_o, (uint32_t)((nkv - 1) & 1));
+    fa_stamp(tr, 20);
     tc_fence_after();
     if (warp_valid) {
       const float inv = 1.f / l_run;
@@ -362,6 +383,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   }
 
+  fa_stamp(tr, 21);
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -369,6 +391,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, FA_TMEM_COLS);
   }
+  fa_stamp(tr, 22);
 }
 
 }  // namespace serenc

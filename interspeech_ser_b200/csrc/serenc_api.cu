@@ -460,13 +460,15 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
   if (h->head_dim == 64 && !h->force_mma_sync_attn) {
     // tcgen05 path: Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
     CUtensorMap tmq, tmkv;
+    AttnParams pt = p;
+    pt.trace = h->gemm_trace;
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
     const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
     if (wavlm)
-      attention_tc_kernel<true><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, p);
+      attention_tc_kernel<true><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, pt);
     else
-      attention_tc_kernel<false><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, p);
+      attention_tc_kernel<false><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, pt);
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -258,8 +258,8 @@ _LAST_MODEL: Dict[str, _Base] = {}
 
 def _resolve_weights(cfg: EncoderConfig, name_or_path: str, random_init: Optional[bool], seed: int):
     cand = []
-    if os.path.isdir(name_or_path) or name_or_path.endswith(".npz"):
-        cand.append(name_or_path)
+    if os.path.isdir(name_or_path) or name_or_path.endswith((".npz", ".pt", ".pth", ".bin", ".safetensors")):
+        cand.append(name_or_path)   # with config_name=...: e.g. a LoRA-tuned classifier state dict (weights.merge_lora)
     root = os.environ.get("SERENC_WEIGHTS_DIR")
     if root:
         cand.append(os.path.join(root, name_or_path))

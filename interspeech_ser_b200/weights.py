@@ -81,10 +81,54 @@ def whisper_sinusoids(length: int, channels: int, max_timescale: float = 10000.0
     return np.ascontiguousarray(np.concatenate([np.sin(t), np.cos(t)], axis=1).astype(np.float32))
 
 
-def from_hf_state_dict(cfg: EncoderConfig, sd: Mapping[str, object]) -> Dict[str, np.ndarray]:
+_LORA_RE = re.compile(r"^(.*)\.lora_([AB])\.([^.]+)\.weight$")
+
+
+def merge_lora(sd: Mapping[str, object], lora_alpha: float = 16.0, adapter: str = "default") -> Dict[str, object]:
+    """Fold peft LoRA adapters into the dense weights:  W <- W + (lora_alpha / r) * B @ A.
+
+    The reference's `*_pretrained` extraction loads a `WavLMClassifier` state dict whose encoder was wrapped by
+    `get_peft_model(LoraConfig(r=8, lora_alpha=16, target_modules=['q_proj', 'v_proj']))`
+    (preprocessing/preprocess_speech_pretrained.py:120-130) and runs `ssl_model.wavlm.model` in eval mode, where the
+    adapter contributes exactly that low-rank term (dropout is off).  peft's key layout is
+    `<wrapper>.base_model.model.<module>.base_layer.weight|bias`, `<module>.lora_A.<adapter>.weight [r, in]`,
+    `<module>.lora_B.<adapter>.weight [out, r]`; the classifier head and other non-encoder keys are dropped.
+    r is read from the adapter's shape; lora_alpha is not stored in a state dict, so the reference's 16 is the default."""
+    plain: Dict[str, object] = {}
+    lora: Dict[str, Dict[str, object]] = {}
+    for k, v in sd.items():
+        if "base_model.model." in k:
+            k = k.split("base_model.model.", 1)[1]
+        elif k.startswith("classifier."):
+            continue
+        m = _LORA_RE.match(k)
+        if m:
+            if m.group(3) == adapter:
+                lora.setdefault(m.group(1), {})[m.group(2)] = v
+            continue
+        plain[k.replace(".base_layer.", ".")] = v
+    for mod, ab in lora.items():
+        if "A" not in ab or "B" not in ab:
+            raise ValueError(f"LoRA adapter for '{mod}' is missing lora_{'B' if 'A' in ab else 'A'}")
+        a, b = _np(ab["A"]).astype(np.float64), _np(ab["B"]).astype(np.float64)
+        if a.shape[0] != b.shape[1]:
+            raise ValueError(f"LoRA rank mismatch for '{mod}': A {a.shape} vs B {b.shape}")
+        key = mod + ".weight"
+        if key not in plain:
+            raise ValueError(f"LoRA adapter for '{mod}' has no base weight")
+        w = _np(plain[key]).astype(np.float64)
+        if w.shape != (b.shape[0], a.shape[1]):
+            raise ValueError(f"LoRA shape mismatch for '{mod}': W {w.shape}, B@A {(b.shape[0], a.shape[1])}")
+        plain[key] = (w + (float(lora_alpha) / a.shape[0]) * (b @ a)).astype(np.float32)
+    return plain
+
+
+def from_hf_state_dict(cfg: EncoderConfig, sd: Mapping[str, object], lora_alpha: float = 16.0) -> Dict[str, np.ndarray]:
     """Convert a HuggingFace state dict (WavLMModel / Wav2Vec2Model / HubertModel / WhisperModel or
-    WhisperEncoder, with or without a task-head prefix) into canonical tensors."""
+    WhisperEncoder, with or without a task-head prefix, with or without peft LoRA adapters) into canonical tensors."""
     sd = dict(sd)
+    if any(".lora_A." in k for k in sd):
+        sd = merge_lora(sd, lora_alpha)
     # strip wrapper prefixes: "wavlm.", "wav2vec2.", "hubert.", "model."
     for prefix in ("wavlm.", "wav2vec2.", "hubert.", "model."):
         if any(k.startswith(prefix) for k in sd):
@@ -225,13 +269,20 @@ def random_init(cfg: EncoderConfig, seed: int = 0) -> Dict[str, np.ndarray]:
 
 
 def load_checkpoint_dir(cfg: EncoderConfig, path: str) -> Dict[str, np.ndarray]:
-    """Load an HF checkpoint directory (model.safetensors or pytorch_model.bin) or a canonical .npz."""
+    """Load an HF checkpoint directory (model.safetensors or pytorch_model.bin), a canonical .npz, or a single
+    torch state-dict file (.pt / .bin / .pth — e.g. the LoRA classifier checkpoint of preprocess_speech_pretrained.py:173)."""
     npz = os.path.join(path, "serenc_weights.npz") if os.path.isdir(path) else path
     if npz.endswith(".npz") and os.path.exists(npz):
         with np.load(npz) as z:
             return {k: np.ascontiguousarray(z[k].astype(np.float32)) for k in z.files}
     import torch
 
+    if os.path.isfile(path) and path.endswith((".pt", ".pth", ".bin")):
+        return from_hf_state_dict(cfg, torch.load(path, map_location="cpu", weights_only=True))
+    if os.path.isfile(path) and path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+
+        return from_hf_state_dict(cfg, load_file(path))
     st_path = os.path.join(path, "model.safetensors")
     bin_path = os.path.join(path, "pytorch_model.bin")
     if os.path.exists(st_path):

@@ -125,6 +125,48 @@ def test_baseline_config0_batching_invariance_and_determinism():
     assert a.shape == (8, 1024) and torch.isfinite(a).all()
 
 
+def test_lora_checkpoint_merged_at_load(tmp_path):
+    """preprocess_speech_pretrained.py:120-178: a peft LoRA (r=8, alpha=16, q_proj/v_proj) classifier state dict,
+    loaded from its .pt file, must give the embeddings of base + adapter (oracle run on independently merged weights)."""
+    from interspeech_ser_b200.modeling import AutoModel
+    from interspeech_ser_b200.weights import from_hf_state_dict
+    cfg = configs.get_config("tiny/wavlm")
+    w = random_init(cfg, 3)
+    rng = np.random.default_rng(5)
+    hf_names = {"q": "q_proj", "k": "k_proj", "v": "v_proj", "o": "out_proj"}
+    merged = {k: v.copy() for k, v in w.items()}
+    sd = {}
+    # hand-built peft layout around the canonical -> HF name map (independent of weights.merge_lora)
+    from oracle.make_golden import hf_model
+    for k, v in hf_model(cfg, w).state_dict().items():
+        mod, leaf = k.rsplit(".", 1)
+        if mod.endswith(("q_proj", "v_proj")):
+            sd[f"wavlm.base_model.model.{mod}.base_layer.{leaf}"] = v
+        else:
+            sd[f"wavlm.base_model.model.{k}"] = v
+    for i in range(cfg.num_hidden_layers):
+        for s_ in ("q", "v"):
+            a = (rng.standard_normal((8, cfg.hidden_size)) * 0.2).astype(np.float32)
+            b = (rng.standard_normal((cfg.hidden_size, 8)) * 0.2).astype(np.float32)
+            mod = f"wavlm.base_model.model.encoder.layers.{i}.attention.{hf_names[s_]}"
+            sd[mod + ".lora_A.default.weight"] = torch.from_numpy(a)
+            sd[mod + ".lora_B.default.weight"] = torch.from_numpy(b)
+            merged[f"layer{i}.{s_}.weight"] = (w[f"layer{i}.{s_}.weight"].astype(np.float64) + 2.0 * (b.astype(np.float64) @ a.astype(np.float64))).astype(np.float32)
+    sd["classifier.0.weight"] = torch.zeros(512, cfg.hidden_size)
+    path = str(tmp_path / "whisper_lora_ser.pt")
+    torch.save(sd, path)
+    model = AutoModel.from_pretrained(path, device=0, config_name="tiny/wavlm")
+    waves = [synth_wave(900 + j, n) for j, n in enumerate((16000, 5000))]
+    res = model.extract(waves, average=True, want_frames=False, want_pooled=True)
+    for b_, wv in enumerate(waves):
+        hs = O.w2v_hidden_states(cfg, merged, wv)
+        ref = torch.stack(hs[-4:]).mean(0)
+        check_embedding(res.pooled[b_], O.masked_mean_pool(ref), f"lora utt{b_}")
+        hs0 = O.w2v_hidden_states(cfg, w, wv)      # the adapter must matter, or this test proves nothing
+        assert float((torch.stack(hs0[-4:]).mean(0) - ref).abs().max()) > 1e-2
+    assert np.allclose(from_hf_state_dict(cfg, sd)["layer1.v.weight"], merged["layer1.v.weight"], atol=1e-6)
+
+
 def test_hf_call_surface_w2v():
     """processor(...) -> model(**inputs, output_hidden_states=True) exactly as preprocess_speech.py:48-67 uses them."""
     from interspeech_ser_b200.modeling import AutoFeatureExtractor

@@ -67,6 +67,51 @@ def test_hf_state_dict_conversion_roundtrip():
             np.testing.assert_allclose(back[k], w[k], rtol=1e-5, atol=1e-6, err_msg=f"{name}:{k}")
 
 
+def test_lora_merge_equals_adapter_forward(tmp_path):
+    """peft-layout state dict (preprocess_speech_pretrained.py:120-130: r=8, alpha=16, q_proj/v_proj) -> dense weights
+    whose Linear output equals base(x) + (alpha/r) * B(A(x)); classifier head dropped; file loading path."""
+    from interspeech_ser_b200.weights import load_checkpoint_dir, merge_lora
+    sys_path_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path_root)
+    pytest.importorskip("transformers")
+    from oracle.make_golden import hf_model
+    cfg = configs.get_config("tiny/wavlm")
+    w = random_init(cfg, 2)
+    sd = hf_model(cfg, w).state_dict()
+    g = torch.Generator().manual_seed(0)
+    peft_sd, expect = {}, {}
+    for k, v in sd.items():
+        mod = k.rsplit(".", 1)[0]
+        if mod.endswith(("q_proj", "v_proj")):
+            peft_sd[f"wavlm.base_model.model.{mod}.base_layer.{k.rsplit('.', 1)[1]}"] = v
+            if k.endswith(".weight"):
+                a = torch.randn(8, v.shape[1], generator=g) * 0.1
+                b = torch.randn(v.shape[0], 8, generator=g) * 0.1
+                peft_sd[f"wavlm.base_model.model.{mod}.lora_A.default.weight"] = a
+                peft_sd[f"wavlm.base_model.model.{mod}.lora_B.default.weight"] = b
+                expect[k] = (a, b, v)
+        else:
+            peft_sd[f"wavlm.base_model.model.{k}"] = v
+    peft_sd["classifier.0.weight"] = torch.zeros(4, 4)
+    merged = merge_lora(peft_sd)
+    assert sorted(merged) == sorted(sd)
+    x = torch.randn(5, cfg.hidden_size, generator=g)
+    for k, (a, b, v) in expect.items():
+        want = x @ v.T + 2.0 * ((x @ a.T) @ b.T)
+        got = x @ torch.from_numpy(np.asarray(merged[k])).T
+        assert torch.allclose(got, want, atol=1e-5, rtol=1e-5), k
+    path = str(tmp_path / "lora_ser.pt")
+    torch.save(peft_sd, path)
+    canon = load_checkpoint_dir(cfg, path)
+    assert sorted(canon) == sorted(w)
+    assert not np.allclose(canon["layer0.q.weight"], w["layer0.q.weight"]) and np.array_equal(canon["layer0.k.weight"], w["layer0.k.weight"])
+    bad = dict(peft_sd)
+    del bad["wavlm.base_model.model.encoder.layers.0.attention.q_proj.lora_B.default.weight"]
+    with pytest.raises(ValueError):
+        merge_lora(bad)
+
+
 def test_mel_filters_and_sinusoids():
     fb = slaney_mel_filters(128)
     assert fb.shape == (201, 128) and fb.min() >= 0 and (fb.max(axis=0) > 0).all()
