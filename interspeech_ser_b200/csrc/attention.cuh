@@ -36,7 +36,12 @@ struct AttnParams {
   const float* gru_b;     // [8]
   const float* gru_const; // [H]
   const float* btab;      // [H, 2*WAVLM_MAXD-1]
-  long long* trace = nullptr;  // debug (serenc_debug_gemm_trace): per-CTA clock stamps of the tcgen05 kernel
+  // tcgen05 kernel only
+  float* gate = nullptr;       // [rows, heads] WavLM gate (wavlm_gate_kernel writes it, attention_tc_kernel reads it)
+  int heads = 0, batch = 0;
+  int ntile = 0;               // 128-query tiles per utterance = ceil(tmax / 128)
+  int nwin = 0;                // stride of one bias-window buffer (entries)
+  long long* trace = nullptr;  // debug (serenc_debug_gemm_trace): per-CTA clock stamps
 };
 
 template <int HD>

@@ -15,7 +15,9 @@
 // shared memory Q 16 KB + K 8 KB + V 8 KB + P 16 KB, single-buffered (K_{j+1} is fetched as soon as S_j is
 // complete, V_{j+1} as soon as O += P_j V_j is). S_{j+1} = Q K_{j+1}^T is issued the moment the softmax threads
 // have finished reading S_j, AHEAD of O += P_j V_j, so that MMA and its commit latency sit under the next row-max
-// pass. FOUR CTAs per SM (<= 80 registers: the softmax makes two passes over S in TMEM instead of holding the
+// pass. WavLM: gate[row, head] comes precomputed (wavlm_gate_kernel), the bias window of the whole query tile is
+// loaded once under the Q/K/V loads, and the biased scores are written back over S so the exp pass does not redo
+// the bias. The running max only moves when it would grow by more than 2^8 (exact), so O is rarely rescaled. FOUR CTAs per SM (<= 80 registers: the softmax makes two passes over S in TMEM instead of holding the
 // row) overlap one CTA's softmax with the others' MMAs and loads.
 // V is consumed as an MN-major (head-dim contiguous) B operand directly from its row-major [key, d] tile.
 #pragma once
@@ -31,13 +33,18 @@ constexpr int FA_THREADS = 160;
 constexpr int FA_Q_BYTES = FA_BM * FA_HD * 2;   // 16 KB
 constexpr int FA_KV_BYTES = FA_BN * FA_HD * 2;  // 8 KB
 constexpr int FA_P_BYTES = FA_BM * FA_BN * 2;   // 16 KB
-constexpr int FA_WIN = FA_BM + FA_BN - 1;       // bias window entries per (q tile, key block)
-constexpr int FA_GW_BYTES = 2 * FA_HD * 4;      // gate weights, pre-summed over the two groups of four outputs
-constexpr int FA_SMEM_BYTES = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + FA_GW_BYTES +
-                              2 * 192 * 4 /*bias windows*/ + 64 /*barriers*/ + 1024;
+constexpr int FA_BAR_BYTES = 64;
+constexpr int FA_SMEM_FIXED = FA_Q_BYTES + 2 * FA_KV_BYTES + FA_P_BYTES + FA_BAR_BYTES + 1024;
+constexpr int FA_SMEM_LIMIT = 227 * 1024;    // opt-in dynamic shared memory of one CTA (bias window of very long utterances)
+// bias-window entries a query tile of an utterance with tmax frames can see (one per (key - query) offset)
+inline int fa_window_entries(int tmax) { return FA_BM + FA_BN * ((tmax + FA_BN - 1) / FA_BN); }
+inline size_t fa_smem_bytes(bool wavlm, int tmax) {
+  return (size_t)FA_SMEM_FIXED + (wavlm ? (size_t)fa_window_entries(tmax) * 4 : 0);
+}
 constexpr int FA_TMEM_COLS = 128;
 constexpr uint32_t FA_WAIT_HINT_NS = 2000;   // softmax threads sleep (NANOSLEEP.SYNCS) instead of spinning on S / O barriers
 constexpr int FA_TMEM_S = 0, FA_TMEM_O = 64;
+constexpr float FA_RESCALE_LOG2 = 8.0f;      // the running max is only raised when it would grow by more than this
 
 // MN-major (N contiguous), 128B-swizzled B operand: 8-row (K) groups are 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
@@ -70,6 +77,49 @@ __device__ __forceinline__ void fa_stamp(long long* tr, int slot) {
   if (tr) tr[slot] = clock64();
 }
 
+// gate[row, head] of WavLM's gated relative position bias (HF modeling_wavlm.py:167-176) from the layer input.
+// Only the SUMS of outputs 0-3 and 4-7 of gru_rel_pos_linear are used (view(.., 2, 4).sum(-1)), so the [8, 64]
+// weight collapses to two 64-vectors. One thread per (row, head): 128 contiguous bytes each, fully coalesced.
+__global__ void __launch_bounds__(256)
+wavlm_gate_kernel(const bf16* __restrict__ hln, int64_t rows, int d, int heads, const float* __restrict__ gru_w,
+                  const float* __restrict__ gru_b, const float* __restrict__ gru_const, float* __restrict__ gate) {
+  __shared__ float4 s_w[FA_HD / 2];   // (wa[k], wb[k], wa[k+1], wb[k+1])
+  __shared__ float s_b[2];
+  if (threadIdx.x < 2 * FA_HD) {
+    const int k = threadIdx.x >> 1, g = threadIdx.x & 1;
+    const float* w = gru_w + g * 4 * FA_HD + k;
+    reinterpret_cast<float*>(s_w)[threadIdx.x] = (__ldg(w) + __ldg(w + FA_HD)) + (__ldg(w + 2 * FA_HD) + __ldg(w + 3 * FA_HD));
+  }
+  if (threadIdx.x < 2) {
+    const float* bb = gru_b + threadIdx.x * 4;
+    s_b[threadIdx.x] = (__ldg(bb) + __ldg(bb + 1)) + (__ldg(bb + 2) + __ldg(bb + 3));
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * heads) return;
+  const int64_t row = i / heads;
+  const int h = (int)(i - row * heads);
+  const uint4* x4 = reinterpret_cast<const uint4*>(hln + row * d + h * FA_HD);
+  uint4 xr[FA_HD / 8];
+#pragma unroll
+  for (int c = 0; c < FA_HD / 8; ++c) xr[c] = __ldg(x4 + c);
+  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < FA_HD / 8; ++c) {
+    const uint32_t uu[4] = {xr[c].x, xr[c].y, xr[c].z, xr[c].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 xv = unpack_bf16x2(uu[e]);
+      const float4 w = s_w[c * 4 + e];
+      a0 = fmaf(xv.x, w.x, a0); b0 = fmaf(xv.x, w.y, b0);
+      a1 = fmaf(xv.y, w.z, a1); b1 = fmaf(xv.y, w.w, b1);
+    }
+  }
+  const float ga = 1.f / (1.f + __expf(-((a0 + a1) + s_b[0])));
+  const float gb = 1.f / (1.f + __expf(-((b0 + b1) + s_b[1])));
+  gate[i] = ga * (gb * __ldg(gru_const + h) - 1.f) + 2.f;
+}
+
 template <bool WAVLM>
 __global__ void __launch_bounds__(FA_THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
@@ -79,9 +129,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + FA_Q_BYTES;
   uint8_t* sV = sK + FA_KV_BYTES;
   uint8_t* sP = sV + FA_KV_BYTES;
-  float4* s_gw = reinterpret_cast<float4*>(sP + FA_P_BYTES);  // [k / 2] = (wa[k], wb[k], wa[k+1], wb[k+1])
-  float* s_win = reinterpret_cast<float*>(sP + FA_P_BYTES + FA_GW_BYTES);  // [2][192]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES + FA_GW_BYTES + 2 * 192 * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES);
+  float* s_win = reinterpret_cast<float*>(sP + FA_P_BYTES + FA_BAR_BYTES);  // WAVLM: [FA_BM + FA_BN * nkv]
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;
   uint64_t* bar_v = bars + 2;
@@ -120,13 +169,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncwarp();
     tmem_alloc(tmem_slot, FA_TMEM_COLS);
     tmem_relinquish();
-  }
-  if (WAVLM && tid < 2 * FA_HD) {
-    // the gate only needs the SUMS of outputs 0-3 and 4-7 of gru_rel_pos_linear (HF modeling_wavlm.py:170-172:
-    // view(.., 2, 4).sum(-1)), so the [8, 64] weight collapses to two 64-vectors
-    const int k = tid >> 1, g = tid & 1;
-    const float* w = p.gru_w + g * 4 * FA_HD + k;
-    reinterpret_cast<float*>(s_gw)[tid] = (__ldg(w) + __ldg(w + FA_HD)) + (__ldg(w + 2 * FA_HD) + __ldg(w + 3 * FA_HD));
   }
   tc_fence_before();
   __syncthreads();
@@ -171,7 +213,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         if (more) {
           // S_{j+1} goes to the tensor core AHEAD of O += P_j V_j: the softmax of block j+1 (its row-max pass only
-          // needs S) starts as soon as possible, and P_j V_j completes underneath it.
+          // needs S) starts as soon as possible, and P_j V_j completes underneath it. (Releasing the S columns even
+          // earlier - once S_j sits in registers - did not pay: the single K tile is then the late one.)
           mbar_wait(bar_k, ph ^ 1u);
           tc_fence_after();
 #pragma unroll
@@ -208,47 +251,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float sc2 = p.scale * LOG2E;
 
     float gate = 0.f;
-    if (WAVLM && row_valid) {
-      // gate (HF modeling_wavlm.py:167-176) from the layer input row of this head
-      const uint4* x4 = reinterpret_cast<const uint4*>(p.hln + (int64_t)(r0 + qi) * p.d + h * FA_HD);
-      float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < FA_HD / 8; ++c) {
-        const uint4 u = __ldg(x4 + c);
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 xv = unpack_bf16x2(uu[e]);
-          const float4 w = s_gw[c * 4 + e];
-          a0 = fmaf(xv.x, w.x, a0); b0 = fmaf(xv.x, w.y, b0);
-          a1 = fmaf(xv.y, w.z, a1); b1 = fmaf(xv.y, w.w, b1);
-        }
+    const float* win = nullptr;
+    if (WAVLM) {
+      // gate[row, head] comes precomputed (wavlm_gate_kernel); the bias window of this query tile is loaded once:
+      // wbuf[x] = bias_h[x - 127 - i0], and row r reads win[key] = wbuf[key + 127 - r]. Both sit under the Q/K/V loads.
+      if (row_valid) gate = __ldg(p.gate + (int64_t)(r0 + qi) * p.heads + h);
+      const float* btab_h = p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1);
+      const int nwin = FA_BM - 1 + FA_BN * nkv;
+      for (int x = tid; x < nwin; x += 128) {
+        int dlt = x - (FA_BM - 1) - i0;
+        dlt = max(-(WAVLM_MAXD - 1), min(WAVLM_MAXD - 1, dlt));   // buckets saturate at |delta| >= 778
+        s_win[x] = __ldg(btab_h + dlt);
       }
-      const float sa = (a0 + a1) + ((__ldg(p.gru_b + 0) + __ldg(p.gru_b + 1)) + (__ldg(p.gru_b + 2) + __ldg(p.gru_b + 3)));
-      const float sb = (b0 + b1) + ((__ldg(p.gru_b + 4) + __ldg(p.gru_b + 5)) + (__ldg(p.gru_b + 6) + __ldg(p.gru_b + 7)));
-      const float ga = 1.f / (1.f + __expf(-sa));
-      const float gb = 1.f / (1.f + __expf(-sb));
-      gate = (ga * (gb * __ldg(p.gru_const + h) - 1.f) + 2.f) * LOG2E;
+      win = s_win + (FA_BM - 1 - row);
+      gate *= LOG2E;
+      softmax_group_sync();
     }
-    const float* btab_h = WAVLM ? p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1) : nullptr;
-
     fa_stamp(tr, 2);
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = (uint32_t)(j & 1);
       const int j0 = j * FA_BN;
       const int ncols = min(FA_BN, T - j0);
-      // bias window of this (query tile, key block): win[x] = bias_h[j0 - i0 - 127 + x], x = col - row + 127
-      const float* win = s_win + (j & 1) * 192 + (FA_BM - 1 - row);   // win[col] == bias_h[(j0 + col) - qi]
-      if (WAVLM) {
-        float* wbuf = s_win + (j & 1) * 192;
-        for (int x = tid; x < FA_WIN; x += 128) {
-          int dlt = j0 - i0 - (FA_BM - 1) + x;
-          dlt = max(-(WAVLM_MAXD - 1), min(WAVLM_MAXD - 1, dlt));   // buckets saturate at |delta| >= 778
-          wbuf[x] = __ldg(btab_h + dlt);
-        }
-        softmax_group_sync();
-      }
       mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_s, ph);
       if (j < 4) fa_stamp(tr, 4 + 4 * j);
       tc_fence_after();
@@ -269,30 +293,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
               for (int k = 0; k < 32; ++k) {
                 float x = __uint_as_float(r[k]);
-                if (WAVLM) x = fmaf(gate, win[c * 32 + k], x * sc2);
+                if (WAVLM) { x = fmaf(gate, win[j0 + c * 32 + k], x * sc2); r[k] = __float_as_uint(x); }
                 m4[k & 3] = fmaxf(m4[k & 3], x);
               }
             } else {
 #pragma unroll
               for (int k = 0; k < 32; ++k) {
                 float x = __uint_as_float(r[k]);
-                if (WAVLM) x = fmaf(gate, win[c * 32 + k], x * sc2);
+                if (WAVLM) { x = fmaf(gate, win[j0 + c * 32 + k], x * sc2); r[k] = __float_as_uint(x); }
                 if (c * 32 + k < ncols) m4[k & 3] = fmaxf(m4[k & 3], x);
               }
             }
+            if (WAVLM) tmem_st_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);   // pass 2 reads x back instead of redoing the bias
             mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
           }
         }
         if (!WAVLM) mx *= sc2;
       }
       if (j < 4) fa_stamp(tr, 5 + 4 * j);
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_new);
+      // lazy running max: keep the old one unless the new maximum exceeds it by more than 2^8 (p stays <= 256,
+      // harmless in bf16 / fp32; sum and O are accumulated against the same m, so the result is exact)
+      const bool raise = (mx > m_run + FA_RESCALE_LOG2);   // also true for the first block (m_run = -inf)
+      const float m_new = raise ? mx : m_run;
+      const float alpha = (j == 0) ? 0.f : fast_exp2(m_run - m_new);   // 1 for lanes that keep their max
 
       if (j > 0) {
         mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_o, ph ^ 1u);  // O += P_{j-1} V_{j-1} complete: O may be rescaled, P overwritten
         tc_fence_after();
-        if (warp_valid && !__all_sync(0xffffffffu, alpha == 1.0f)) {
+        if (warp_valid && __any_sync(0xffffffffu, raise)) {
 #pragma unroll
           for (int c = 0; c < FA_HD / 32; ++c) {
             uint32_t r[32];
@@ -302,49 +330,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
             tmem_st_32x32b_x32(t_lane + FA_TMEM_O + c * 32, r);
           }
-          tmem_st_wait();
         }
       }
+      if (WAVLM || j > 0) tmem_st_wait();
 
       if (j < 4) fa_stamp(tr, 6 + 4 * j);
       // pass 2: p = exp2(x - m), row sum, P (bf16) -> shared memory (K-major SW128: chunk = key / 8, XOR row % 8)
       float rs = 0.f;
+      const bool two = FA_BN / 2 < ncols;   // CTA-uniform: the second 32-column chunk holds valid keys
+      const float neg_m = -m_new;
+      auto chunk = [&](uint32_t (&r)[32], const int c) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float x = __uint_as_float(r[k]);
+          float e;
+          if (WAVLM) e = fast_exp2(x + neg_m);
+          else e = fast_exp2(fmaf(x, sc2, neg_m));
+          if (!full && c * 32 + k >= ncols) e = 0.f;
+          s4[k & 3] += e;
+          r[k] = __float_as_uint(e);
+        }
+        rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+#pragma unroll
+        for (int k8 = 0; k8 < 4; ++k8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]), __uint_as_float(r[k8 * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]), __uint_as_float(r[k8 * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]), __uint_as_float(r[k8 * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]), __uint_as_float(r[k8 * 8 + 7]));
+          const int ch = c * 4 + k8;
+          *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
+        }
+      };
       if (warp_valid) {
-        const float neg_m = -m_new;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_lane + FA_TMEM_S, r);
+        tmem_ld_wait();
+        chunk(r, 0);
+        if (two) {
+          tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + 32, r);
+          tmem_ld_wait();
+          chunk(r, 1);
+        } else {
 #pragma unroll
-        for (int c = 0; c < FA_BN / 32; ++c) {
-          if (c * 32 < ncols) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
-            tmem_ld_wait();
-            float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              float x = __uint_as_float(r[k]);
-              float e;
-              if (WAVLM) e = fast_exp2(fmaf(gate, win[c * 32 + k], fmaf(x, sc2, neg_m)));
-              else e = fast_exp2(fmaf(x, sc2, neg_m));
-              if (!full && c * 32 + k >= ncols) e = 0.f;
-              s4[k & 3] += e;
-              r[k] = __float_as_uint(e);
-            }
-            rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              uint4 u;
-              u.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]), __uint_as_float(r[k8 * 8 + 1]));
-              u.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]), __uint_as_float(r[k8 * 8 + 3]));
-              u.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]), __uint_as_float(r[k8 * 8 + 5]));
-              u.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]), __uint_as_float(r[k8 * 8 + 7]));
-              const int ch = c * 4 + k8;
-              *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
-            }
-          } else {
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              const int ch = c * 4 + k8;
-              *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-            }
+          for (int k8 = 0; k8 < 4; ++k8) {
+            const int ch = 4 + k8;
+            *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
           }
         }
       }

@@ -462,13 +462,22 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     CUtensorMap tmq, tmkv;
     AttnParams pt = p;
     pt.trace = h->gemm_trace;
+    pt.heads = h->cfg.heads; pt.batch = batch;
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
+    const size_t smem = fa_smem_bytes(wavlm, tmax);
+    if (smem > FA_SMEM_LIMIT) SERENC_FAIL(SERENC_ERR_INVALID, "attention: utterance of %d frames exceeds the bias-window capacity", tmax);
     const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
-    if (wavlm)
-      attention_tc_kernel<true><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, pt);
-    else
-      attention_tc_kernel<false><<<grid, block, FA_SMEM_BYTES, st>>>(tmq, tmkv, pt);
+    if (wavlm) {
+      if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
+      const int64_t nthr = sum_rows * h->cfg.heads;
+      wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
+      SERENC_CUDA_OK(cudaGetLastError());
+      h->launches += 1;
+      attention_tc_kernel<true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+    } else {
+      attention_tc_kernel<false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+    }
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -700,8 +709,8 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
-    attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
-    attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
   }
   if (st) {
     serenc_destroy(h);
@@ -951,6 +960,7 @@ struct StackBufs {
   bf16* qkv;    // [sumT, 3d]
   bf16* att;    // [sumT, d]
   bf16* ffn;    // [sumT, ffn]
+  float* gate = nullptr;  // [sumT, heads] WavLM gate of the current layer
 };
 
 // Pre-LN ("stable layer norm") encoder stack + final LayerNorm, emitting the selected hidden states.
@@ -973,7 +983,7 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
       AttnParams p;
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
-      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
     {
@@ -1023,7 +1033,7 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
       AttnParams p;
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
-      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
     {
@@ -1135,6 +1145,7 @@ void carve_w2v(const serenc_handle* h, const W2VPlan& p, void* base, W2VWs* w) {
   w->sb.hln = cv.take<bf16>((size_t)p.sumT * d);
   w->sb.qkv = cv.take<bf16>((size_t)p.sumT * 3 * d);
   w->sb.att = cv.take<bf16>((size_t)p.sumT * d);
+  w->sb.gate = c.wavlm_rel_bias ? cv.take<float>((size_t)p.sumT * c.heads) : nullptr;
   w->sb.ffn = cv.take<bf16>((size_t)p.sumT * c.ffn);
   w->acc = cv.take<float>((size_t)p.sumT * d);
   w->bytes = cv.used();
@@ -1589,5 +1600,8 @@ extern "C" int serenc_op_attention(serenc_handle* h, const void* qkv, const int6
   p.hln = reinterpret_cast<const bf16*>(hln);
   const LayerW& l = h->L[wavlm ? layer : 0];
   p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab;
-  return launch_attn(h, p, wavlm != 0, tmax, batch, frame_offsets[batch], 0.0, st);
+  if (wavlm) SERENC_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&p.gate), sizeof(float) * (size_t)frame_offsets[batch] * h->cfg.heads, st));
+  const int rc = launch_attn(h, p, wavlm != 0, tmax, batch, frame_offsets[batch], 0.0, st);
+  if (wavlm) SERENC_CUDA_OK(cudaFreeAsync(p.gate, st));
+  return rc;
 }

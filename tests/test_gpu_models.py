@@ -139,7 +139,7 @@ def test_lora_checkpoint_merged_at_load(tmp_path):
     # hand-built peft layout around the canonical -> HF name map (independent of weights.merge_lora)
     from oracle.make_golden import hf_model
     for k, v in hf_model(cfg, w).state_dict().items():
-        mod, leaf = k.rsplit(".", 1)
+        mod, _, leaf = k.rpartition(".")
         if mod.endswith(("q_proj", "v_proj")):
             sd[f"wavlm.base_model.model.{mod}.base_layer.{leaf}"] = v
         else:
