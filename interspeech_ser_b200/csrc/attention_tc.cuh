@@ -178,36 +178,50 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 4) {
     // ------------------------------ control: TMA + MMA issue ------------------------------
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform operands and ONE elected lane issues (see elect_one_sync in
+    // common.cuh: from inside `if (lane == 0)` every UTCHMMA / UTMALDG costs an elect + R2UR waterfall, ~100 cycles,
+    // which with N = 64 MMAs was most of this thread's time).
+    {
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const int r0u = (int)warp_uniform((uint32_t)r0);
+      const int nkv = (int)warp_uniform((uint32_t)((T + FA_BN - 1) / FA_BN));   // shadows the CTA-wide value: uniform for the compiler
       const int colq = h * FA_HD, colk = p.d + h * FA_HD, colv = 2 * p.d + h * FA_HD;
-      mbar_arrive_expect_tx(bar_q, FA_Q_BYTES);
-      tma_load_2d(sQ, &tmQ, bar_q, colq, r0 + i0);
-      mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
-      tma_load_2d(sK, &tmKV, bar_k, colk, r0);
-      mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
-      tma_load_2d(sV, &tmKV, bar_v, colv, r0);
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);                 // Q K^T: both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(FA_BM, FA_HD) | (1u << 16);    // P V: B (= V) MN-major
       const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sK));
       const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
+      const uint64_t vdesc = umma_desc_sw128_mn(smem_u32(sV));
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar_q, FA_Q_BYTES);
+        tma_load_2d(sQ, &tmQ, bar_q, colq, r0u + i0);
+        mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
+        tma_load_2d(sK, &tmKV, bar_k, colk, r0u);
+        mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
+        tma_load_2d(sV, &tmKV, bar_v, colv, r0u);
+      }
+      __syncwarp();
       mbar_wait(bar_q, 0);
       fa_stamp(tr, 2);
       mbar_wait(bar_k, 0);
       tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < FA_HD / 16; ++k)
-        umma_bf16_ss(tmem_base + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-      umma_commit(bar_s);
+        for (int k = 0; k < FA_HD / 16; ++k)
+          umma_bf16_ss(tmem_u + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+        umma_commit(bar_s);
+      }
+      __syncwarp();
       for (int j = 0; j < nkv; ++j) {
         const uint32_t ph = (uint32_t)(j & 1);
         const bool more = j + 1 < nkv;
         mbar_wait(bar_s, ph);  // S_j complete => K tile free
         if (j < 4) fa_stamp(tr, 4 + 4 * j);
-        if (more) {
+        if (more && elect_one_sync()) {
           mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
-          tma_load_2d(sK, &tmKV, bar_k, colk, r0 + (j + 1) * FA_BN);
+          tma_load_2d(sK, &tmKV, bar_k, colk, r0u + (j + 1) * FA_BN);
         }
+        __syncwarp();
         mbar_wait(bar_p, ph);  // P_j in shared memory, every softmax thread is done reading S_j, O rescaled
         if (j < 4) fa_stamp(tr, 5 + 4 * j);
         tc_fence_after();
@@ -217,26 +231,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // earlier - once S_j sits in registers - did not pay: the single K tile is then the late one.)
           mbar_wait(bar_k, ph ^ 1u);
           tc_fence_after();
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < FA_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-          umma_commit(bar_s);
+            for (int k = 0; k < FA_HD / 16; ++k)
+              umma_bf16_ss(tmem_u + FA_TMEM_S, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+            umma_commit(bar_s);
+          }
+          __syncwarp();
         }
         mbar_wait(bar_v, ph);
         if (j < 4) fa_stamp(tr, 6 + 4 * j);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k = 0; k < FA_BN / 16; ++k) {
-          // A = P: +32 B per 16 keys inside the swizzle row; B = V (MN-major): 16 keys = 16 rows of 128 B
-          const uint64_t bdesc = umma_desc_sw128_mn(smem_u32(sV + k * 16 * 128));
-          umma_bf16_ss(tmem_base + FA_TMEM_O, pdesc + (uint64_t)(2 * k), bdesc, idesc_o, (uint32_t)((j | k) != 0));
+          for (int k = 0; k < FA_BN / 16; ++k) {
+            // A = P: +32 B per 16 keys inside the swizzle row; B = V (MN-major): 16 keys = 16 rows of 128 B
+            umma_bf16_ss(tmem_u + FA_TMEM_O, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(k * (16 * 128 >> 4)), idesc_o, (uint32_t)((j | k) != 0));
+          }
+          umma_commit(bar_o);
         }
-        umma_commit(bar_o);
+        __syncwarp();
         if (more) {
           mbar_wait(bar_o, ph);  // O += P_j V_j complete => V tile free
           if (j < 4) fa_stamp(tr, 7 + 4 * j);
-          mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
-          tma_load_2d(sV, &tmKV, bar_v, colv, r0 + (j + 1) * FA_BN);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
+            tma_load_2d(sV, &tmKV, bar_v, colv, r0u + (j + 1) * FA_BN);
+          }
+          __syncwarp();
         }
       }
     }

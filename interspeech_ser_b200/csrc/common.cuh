@@ -180,6 +180,25 @@ __device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
   return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
 }
 
+// One elected lane of a CONVERGED warp. The single-thread tcgen05 / TMA instructions take their operands from
+// uniform registers; issued from inside an `if (lane == 0)` region the compiler cannot prove the operands
+// warp-uniform and wraps every UTCHMMA / UTMALDG in an elect + 5 x R2UR "waterfall" loop (~100 cycles per
+// instruction, measured: it made every MMA narrower than N = 256 issue-bound). Role warps therefore run their
+// loops with all 32 lanes (uniform control flow, uniform operands) and only predicate the issue itself.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, marked warp-uniform for the compiler
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------

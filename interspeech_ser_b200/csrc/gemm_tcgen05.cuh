@@ -63,7 +63,7 @@ struct GemmParams {
   bf16* out_bf16;        // may be nullptr
   int64_t ld_bf16;
   const int32_t* rowmap; // [M] -> output row, <0 = skip; nullptr = identity
-  int act;               // 0 = none, 1 = exact GELU (applied before the residual add)
+  int act;               // 0 = none, 1 = exact GELU (applied before the residual add), 2 = ReLU (bf16 path, microbenchmarks only)
   long long* trace;      // debug: per-tile clock64 stamps of CTA 0 ([tile][8]); nullptr in production
 };
 
@@ -163,6 +163,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
           if (p.act == 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
+          } else if (p.act == 2) {   // ReLU: microbenchmark control only (tests/bench_epilogue.py), no model uses it
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           uint4 u;
           u.x = pack_bf16x2(v[0], v[1]);
@@ -310,8 +313,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;
 
   if (warp == GEMM_WARP_TMA) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (whole warp, one elected lane issues) ------------------------------
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -320,16 +323,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
         const int wrow0 = tc.g * p.n_per_group + tc.n_t * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int tap = kb / p.a_kpt;
           const int cc = kb - tap * p.a_kpt;
           const int acol = tc.g * p.a_group_stride + cc * GEMM_BK;
-          if (p.a_stride == 2) {
-            tma_load_2d(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, &full_bar[stage], acol, m0 + (tap >> 1));
-          } else {
-            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA0, &full_bar[stage], acol, m0 + tap);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (p.a_stride == 2) {
+              tma_load_2d(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, &full_bar[stage], acol, m0 + (tap >> 1));
+            } else {
+              tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA0, &full_bar[stage], acol, m0 + tap);
+            }
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, wrow0);
           }
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * GEMM_BK, wrow0);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -338,9 +344,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       }
     }
   } else if (warp == GEMM_WARP_MMA) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (whole warp, one elected lane issues) ------------------------------
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -348,25 +355,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // +32 B per UMMA_K step inside the 128 B swizzle row: start-address field advances by 2
-            umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                         (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              // +32 B per UMMA_K step inside the 128 B swizzle row: start-address field advances by 2
+              umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                           (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (elect_one_sync()) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -423,7 +434,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();   // 0 = leader (issues the MMAs), 1 = peer
+  const uint32_t rank = warp_uniform(cluster_ctarank());   // 0 = leader (issues the MMAs), 1 = peer
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
 
@@ -455,27 +466,31 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;   // tiles_m counts 256-row tiles here
 
   if (warp == GEMM_WARP_TMA) {
-    // ------------------------------ TMA producer (both CTAs) ------------------------------
-    if (lane == 0) {
+    // ------------------------------ TMA producer (both CTAs; whole warp, one elected lane issues) ------------------------------
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t leader_bar0 = warp_uniform(mapa_shared(smem_u32(&full_bar[0]), 0));   // leader's full_bar[0]
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const TileCoord tc = decode_tile(p, tile);
         const int m0 = tc.m_t * (2 * GEMM_BM) + (int)rank * GEMM_BM;
         const int wrow0 = tc.g * p.n_per_group + tc.n_t * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          const uint32_t leader_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const uint32_t leader_bar = leader_bar0 + (uint32_t)(stage * 8);
           const int tap = kb / p.a_kpt;
           const int cc = kb - tap * p.a_kpt;
           const int acol = tc.g * p.a_group_stride + cc * GEMM_BK;
-          if (p.a_stride == 2) {
-            tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, leader_bar, acol, m0 + (tap >> 1));
-          } else {
-            tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &tmA0, leader_bar, acol, m0 + tap);
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            if (p.a_stride == 2) {
+              tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, (tap & 1) ? &tmA1 : &tmA0, leader_bar, acol, m0 + (tap >> 1));
+            } else {
+              tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &tmA0, leader_bar, acol, m0 + tap);
+            }
+            tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, &tmB, leader_bar, kb * GEMM_BK, wrow0);
           }
-          tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, &tmB, leader_bar, kb * GEMM_BK, wrow0);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -484,39 +499,45 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
       }
     }
   } else if (warp == GEMM_WARP_MMA) {
-    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-    if (lane == 0 && rank == 0) {
+    // ------------------------------ MMA issuer (leader CTA only; whole warp, one elected lane issues) ------------------------------
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      const uint32_t tmem_u = warp_uniform(tmem_base);
+      const bool tracing = p.trace && blockIdx.x == 0 && lane == 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
-        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 0] = clock64();
+        if (tracing) p.trace[it * 8 + 0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 1] = clock64();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        if (tracing) p.trace[it * 8 + 1] = clock64();
+        const uint32_t d_tmem = tmem_u + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == 0 && p.trace && blockIdx.x == 0) p.trace[it * 8 + 2] = clock64();
+          if (kb == 0 && tracing) p.trace[it * 8 + 2] = clock64();
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                              (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              umma_bf16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (uint32_t)((kb | k) != 0));
+            }
+            umma_commit_2cta(&empty_bar[stage]);  // frees this smem slot in BOTH CTAs
           }
-          umma_commit_2cta(&empty_bar[stage]);  // frees this smem slot in BOTH CTAs
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit_2cta(&tfull_bar[acc]);  // accumulator complete, signalled to both CTAs' epilogues
-        if (p.trace && blockIdx.x == 0) p.trace[it * 8 + 3] = clock64();
+        if (elect_one_sync()) umma_commit_2cta(&tfull_bar[acc]);  // accumulator complete, signalled to both CTAs' epilogues
+        __syncwarp();
+        if (tracing) p.trace[it * 8 + 3] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

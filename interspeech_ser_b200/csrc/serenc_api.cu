@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "frontend_norm.cuh"
 #include "gemm_tcgen05.cuh"
+#include "posconv_tcgen05.cuh"
 #include "logmel.cuh"
 
 using namespace serenc;
@@ -106,6 +107,8 @@ struct serenc_handle {
   bool prof = false;
   long long* gemm_trace = nullptr;  // debug: device buffer for per-tile clock stamps of the CTA-pair GEMM (serenc_debug_gemm_trace)
   bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
+  bool no_posconv_slab = false;   // SERENC_NO_POSCONV_SLAB=1: positional conv through the generic implicit GEMM
+  int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
   bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: head_dim-64 attention on the mma.sync kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
@@ -368,10 +371,58 @@ int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   return 0;
 }
 
+// stride-1 grouped convolution with many taps (the positional conv embedding): slab-reuse kernel
+template <int BN>
+int launch_posconv_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
+  using S = PosConvSmem<BN>;
+  PosConvCfg cfg;
+  cfg.taps = c.taps;
+  cfg.kpt = c.a_kpt;
+  cfg.slab_rows = ((PC_BM + c.taps - 1 + 127) / 128) * 128;
+  cfg.slab_bufs = 2;
+  if (S::bytes(cfg) > (size_t)h->max_smem) cfg.slab_bufs = 1;
+  if (S::bytes(cfg) > (size_t)h->max_smem) return -1000;   // caller falls back to the generic implicit GEMM
+  GemmParams p;
+  p.M = c.M;
+  p.n_per_group = c.n_per_group;
+  p.groups = c.groups;
+  p.num_kb = c.taps * c.a_kpt;
+  p.tiles_m = (int)ceil_div64(c.M, PC_BM);
+  p.tiles_n = 1;
+  p.a_kpt = c.a_kpt;
+  p.a_stride = 1;
+  p.a_group_stride = c.a_group_stride;
+  p.bias = c.bias; p.resid = c.resid; p.out_f32 = c.out_f32; p.ld_f32 = c.ld_f32;
+  p.out_bf16 = c.out_bf16; p.ld_bf16 = c.ld_bf16; p.rowmap = c.rowmap; p.act = c.act; p.trace = nullptr;
+  CUtensorMap tA, tW;
+  SERENC_TRY(get_tmap(h, c.A, (uint64_t)c.a_cols, (uint64_t)c.a_rows, (uint64_t)c.a_ld * 2, GEMM_BM, &tA));
+  const uint64_t wk = c.w_k > 0 ? (uint64_t)c.w_k : (uint64_t)p.num_kb * GEMM_BK;
+  SERENC_TRY(get_tmap(h, c.W, wk, (uint64_t)c.w_rows, wk * 2, BN, &tW));
+  const int64_t tiles = (int64_t)p.tiles_m * p.groups;
+  if (tiles <= 0) return 0;
+  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  const double flops = c.alg_flops >= 0 ? c.alg_flops : 2.0 * (double)c.M * c.n_per_group * c.groups * p.num_kb * GEMM_BK;
+  const double bytes = 2.0 * ((double)c.M * c.a_cols + (double)c.w_rows * p.num_kb * GEMM_BK) +
+                       (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
+  static bool attr_set = false;   // opt-in shared memory once per process and instantiation
+  if (!attr_set) {
+    SERENC_CUDA_OK(cudaFuncSetAttribute(posconv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    attr_set = true;
+  }
+  ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
+  posconv_tcgen05_kernel<BN><<<grid, GEMM_THREADS, S::bytes(cfg), st>>>(tA, tW, p, cfg);
+  SERENC_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_gemm(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   if (c.n_per_group % 8 != 0) SERENC_FAIL(SERENC_ERR_INVALID, "gemm: output width %d not a multiple of 8", c.n_per_group);
   if ((c.a_ld % 8) != 0 || (c.a_group_stride % 8) != 0 || (c.w_k % 8) != 0)
     SERENC_FAIL(SERENC_ERR_INVALID, "gemm: A leading dimension must be a multiple of 8 elements");
+  if (c.groups > 1 && c.taps >= 8 && c.a_stride == 1 && c.n_per_group <= 128 && c.out_f32 && !h->no_posconv_slab) {
+    const int rc = c.n_per_group <= 64 ? launch_posconv_bn<64>(h, c, st) : launch_posconv_bn<128>(h, c, st);
+    if (rc != -1000) return rc;
+  }
   if (c.n_per_group <= 64) return launch_gemm_bn<64>(h, c, st);
   // wide outputs with enough work for the CTA pairs: 256 x 256 tiles on tcgen05.mma.cta_group::2
   const int64_t tiles2 = ceil_div64(c.M, 2 * GEMM_BM) * ceil_div(c.n_per_group, GEMM2_BN) * c.groups;
@@ -656,6 +707,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->num_sms = prop.multiProcessorCount;
   h->head_dim = hd;
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   *out = h;
 
