@@ -37,7 +37,8 @@ struct AttnParams {
   const float* gru_const; // [H]
   const float* btab;      // [H, 2*WAVLM_MAXD-1]
   // tcgen05 kernel only
-  float* gate = nullptr;       // [rows, heads] WavLM gate (wavlm_gate_kernel writes it, attention_tc_kernel reads it)
+  float* gate = nullptr;       // [rows, heads] WavLM gate (LayerNorm epilogue or wavlm_gate_kernel writes it, attention_tc_kernel reads it)
+  bool gate_ready = false;     // the LayerNorm that produced hln already filled `gate`
   int heads = 0, batch = 0;
   int ntile = 0;               // 128-query tiles per utterance = ceil(tmax / 128)
   int nwin = 0;                // stride of one bias-window buffer (entries)

@@ -288,6 +288,15 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+// WavLM gate fused into the LayerNorm that produces the attention input (HF modeling_wavlm.py:167-176):
+// gate[row, head] = a * (b * const_head - 1) + 2,  (a, b) = sigmoid(sums of outputs 0-3 / 4-7 of gru_rel_pos_linear).
+struct LnGate {
+  const float* w2 = nullptr;      // [2, 64] the 8 x 64 weight summed over each group of four outputs
+  const float* b2 = nullptr;      // [2]
+  const float* gconst = nullptr;  // [heads]
+  float* out = nullptr;           // [rows, heads], heads = row width / 64
+};
+
 // Rows per warp: narrow rows give a warp too little to do per trip to HBM, so it keeps several rows in flight.
 template <int NV>
 struct LnRows {
@@ -301,13 +310,26 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
                                                               const float* __restrict__ beta, int64_t rows,
                                                               const int32_t* __restrict__ in_rowmap,
                                                               const int32_t* __restrict__ out_rowmap, float eps,
-                                                              bf16* __restrict__ out2 = nullptr, int64_t ld_out2 = 0) {
+                                                              bf16* __restrict__ out2 = nullptr, int64_t ld_out2 = 0,
+                                                              const LnGate gate = LnGate()) {
   // out2: optional second, bf16 copy of the result (post-LN layers: the fp32 residual stream is normalised in place
   // and the same values feed the next GEMM)
+  // gate: optional WavLM gate of the NEXT attention (head_dim 64: the 2 heads of a 128-column chunk are its two
+  // half-warps), computed from the fp32 normalised row that is in registers anyway
   constexpr int RPW = LnRows<NV>::RPW;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
+  // gate constants first: their (L2) latency must overlap the row loads, not follow the statistics
+  float4 gwa = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gwa;
+  float gb0 = 0.f, gb1 = 0.f, gcst = 0.f;
+  if (NV <= 8 && gate.out) {   // this lane's 4 columns of every chunk sit at offset 4 * (lane % 16) inside their head
+    gwa = __ldg(reinterpret_cast<const float4*>(gate.w2 + 4 * (lane & 15)));
+    gwb = __ldg(reinterpret_cast<const float4*>(gate.w2 + 64 + 4 * (lane & 15)));
+    gb0 = __ldg(gate.b2);
+    gb1 = __ldg(gate.b2 + 1);
+    if ((lane & 15) < NV) gcst = __ldg(gate.gconst + 2 * (lane & 15) + (lane >> 4));
+  }
   int64_t irow[RPW], orow[RPW];
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
@@ -342,6 +364,9 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
     }
     rs[r] = rsqrtf(warp_sum(q) * invC + eps);
   }
+  // gate partials: after the first exchange (xor 8) lanes with bit 3 clear carry a_i, lanes with bit 3 set b_i
+  float gu[RPW][NV <= 8 ? NV : 1];
+  const bool ghi = (lane & 8) != 0;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 4;
@@ -349,8 +374,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
     const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-      if (orow[r] < 0) continue;
-      float4 o;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (orow[r] >= 0) {
       o.x = (v[r][i].x - mu[r]) * rs[r] * g.x + be.x;
       o.y = (v[r][i].y - mu[r]) * rs[r] * g.y + be.y;
       o.z = (v[r][i].z - mu[r]) * rs[r] * g.z + be.z;
@@ -360,6 +385,41 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
       }
       store4<TOut>(out + orow[r] * ld_out + c, o);
       if (out2) store4<bf16>(out2 + orow[r] * ld_out2 + c, o);
+      }
+      if (NV <= 8 && gate.out) {
+        const float a = (o.x * gwa.x + o.y * gwa.y) + (o.z * gwa.z + o.w * gwa.w);
+        const float b = (o.x * gwb.x + o.y * gwb.y) + (o.z * gwb.z + o.w * gwb.w);
+        gu[r][NV <= 8 ? i : 0] = (ghi ? b : a) + __shfl_xor_sync(0xffffffffu, ghi ? a : b, 8);
+      }
+    }
+  }
+  if (NV <= 8 && gate.out) {   // WavLM has head_dim 64 and at most 16 heads
+    // Head 2 i + (lane / 16) needs its partial sums added over the 16 lanes of its half-warp. The remaining values
+    // are reduced TRANSPOSED: at every step a lane hands half of its values to its partner and keeps the other half,
+    // so 4 + 2 + 1 more shuffles leave a_i (b_i) fully summed in lane i (8 + i) of the half-warp.
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = i < NV ? gu[r][i < NV && NV <= 8 ? i : 0] : 0.f;
+#pragma unroll
+      for (int w = 4; w > 0; w >>= 1) {
+        const bool hi = (lane & w) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+          const float send = hi ? t[j] : t[j + w];
+          const float keep = hi ? t[j + w] : t[j];
+          t[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+      }
+      const float sb = __shfl_xor_sync(0xffffffffu, t[0], 8);   // b_i from lane 8 + i
+      const int i = lane & 15;
+      if (orow[r] >= 0 && i < NV) {
+        const int head = 2 * i + (lane >> 4);
+        const float s0 = 1.f / (1.f + __expf(-(t[0] + gb0)));
+        const float s1 = 1.f / (1.f + __expf(-(sb + gb1)));
+        gate.out[orow[r] * (2 * NV) + head] = s0 * (s1 * gcst - 1.f) + 2.f;
+      }
     }
   }
 }

@@ -63,7 +63,7 @@ struct GemmParams {
   bf16* out_bf16;        // may be nullptr
   int64_t ld_bf16;
   const int32_t* rowmap; // [M] -> output row, <0 = skip; nullptr = identity
-  int act;               // 0 = none, 1 = exact GELU (applied before the residual add), 2 = ReLU (bf16 path, microbenchmarks only)
+  int act;               // 0 = none, 1 = exact GELU (applied before the residual add)
   long long* trace;      // debug: per-tile clock64 stamps of CTA 0 ([tile][8]); nullptr in production
 };
 
@@ -163,9 +163,6 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
           if (p.act == 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
-          } else if (p.act == 2) {   // ReLU: microbenchmark control only (tests/bench_epilogue.py), no model uses it
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
           uint4 u;
           u.x = pack_bf16x2(v[0], v[1]);

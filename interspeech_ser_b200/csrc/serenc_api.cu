@@ -60,6 +60,7 @@ struct LayerW {
   bf16* w_fc2;  // [d, ffn]
   float* b_fc2;
   float *gru_w, *gru_b, *gru_const;  // WavLM: [8, hd], [8], [H]
+  float *gru_w2, *gru_b2;            // WavLM: the same, summed over the two groups of four outputs: [2, hd], [2]
 };
 
 static const int W2V_K[7] = {10, 3, 3, 3, 3, 2, 2};
@@ -454,7 +455,8 @@ GemmCall linear_call(const bf16* A, int64_t M, int K, const bf16* W, int N) {
 // ---------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut, bool GELU>
 int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64_t ld_out, const float* g, const float* b, int64_t rows,
-                int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st, bf16* out2 = nullptr) {
+                int cols, const int32_t* in_map, const int32_t* out_map, float eps, cudaStream_t st, bf16* out2 = nullptr,
+                const LnGate& gate = LnGate()) {
   if (rows <= 0) return 0;
   const int nv = cols / 128;
   const dim3 block(256);
@@ -462,7 +464,7 @@ int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64
 #define SERENC_LN_CASE(NV)                                                                                         \
   case NV:                                                                                                         \
     layernorm_rows_kernel<NV, TIn, TOut, GELU><<<dim3((unsigned)ceil_div64(rows, 8 * LnRows<NV>::RPW)), block, 0, st>>>( \
-        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps, out2, (int64_t)cols);                           \
+        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps, out2, (int64_t)cols, gate);                     \
     break;
   switch (nv) {
     SERENC_LN_CASE(1)
@@ -521,10 +523,12 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
     if (wavlm) {
       if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
-      const int64_t nthr = sum_rows * h->cfg.heads;
-      wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
-      SERENC_CUDA_OK(cudaGetLastError());
-      h->launches += 1;
+      if (!p.gate_ready) {   // stand-alone entry (serenc_op_attention); the encoder stacks fuse the gate into the LayerNorm
+        const int64_t nthr = sum_rows * h->cfg.heads;
+        wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
+        SERENC_CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+      }
       attention_tc_kernel<true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
     } else {
       attention_tc_kernel<false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
@@ -720,8 +724,8 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     A(&l.w_o, (size_t)d * d); A(&l.b_o, d);
     A(&l.w_fc1, (size_t)cfg->ffn * d); A(&l.b_fc1, cfg->ffn);
     A(&l.w_fc2, (size_t)d * cfg->ffn); A(&l.b_fc2, d);
-    l.gru_w = l.gru_b = l.gru_const = nullptr;
-    if (cfg->wavlm_rel_bias) { A(&l.gru_w, 8 * hd); A(&l.gru_b, 8); A(&l.gru_const, cfg->heads); }
+    l.gru_w = l.gru_b = l.gru_const = l.gru_w2 = l.gru_b2 = nullptr;
+    if (cfg->wavlm_rel_bias) { A(&l.gru_w, 8 * hd); A(&l.gru_b, 8); A(&l.gru_const, cfg->heads); A(&l.gru_w2, 2 * hd); A(&l.gru_b2, 2); }
   }
   A(&h->fin_g, d); A(&h->fin_b, d);
   if (cfg->arch == SERENC_ARCH_W2V) {
@@ -834,8 +838,23 @@ extern "C" int serenc_load_tensor(serenc_handle* h, const char* name, const floa
     else if (s == "fc1.bias") { SERENC_TRY(expect(c.ffn)); st = upload_f32(l.b_fc1, data, n); }
     else if (s == "fc2.weight") { SERENC_TRY(expect((int64_t)c.ffn * d)); st = upload_bf16(l.w_fc2, to_bf16(data, n)); }
     else if (s == "fc2.bias") { SERENC_TRY(expect(d)); st = upload_f32(l.b_fc2, data, n); }
-    else if (c.wavlm_rel_bias && s == "gru.weight") { SERENC_TRY(expect(8 * hd)); st = upload_f32(l.gru_w, data, n); }
-    else if (c.wavlm_rel_bias && s == "gru.bias") { SERENC_TRY(expect(8)); st = upload_f32(l.gru_b, data, n); }
+    else if (c.wavlm_rel_bias && s == "gru.weight") {
+      SERENC_TRY(expect(8 * hd));
+      st = upload_f32(l.gru_w, data, n);
+      // the gate only uses view(.., 2, 4).sum(-1) of the 8 outputs (HF modeling_wavlm.py:170-172): two hd-vectors
+      std::vector<float> w2((size_t)2 * hd);
+      for (int g2 = 0; g2 < 2; ++g2)
+        for (int k = 0; k < hd; ++k)
+          w2[(size_t)g2 * hd + k] = (data[(size_t)(4 * g2) * hd + k] + data[(size_t)(4 * g2 + 1) * hd + k]) +
+                                    (data[(size_t)(4 * g2 + 2) * hd + k] + data[(size_t)(4 * g2 + 3) * hd + k]);
+      if (st == 0) st = upload_f32(l.gru_w2, w2.data(), w2.size());
+    }
+    else if (c.wavlm_rel_bias && s == "gru.bias") {
+      SERENC_TRY(expect(8));
+      st = upload_f32(l.gru_b, data, n);
+      const float b2[2] = {(data[0] + data[1]) + (data[2] + data[3]), (data[4] + data[5]) + (data[6] + data[7])};
+      if (st == 0) st = upload_f32(l.gru_b2, b2, 2);
+    }
     else if (c.wavlm_rel_bias && s == "gru.const") { SERENC_TRY(expect(c.heads)); st = upload_f32(l.gru_const, data, n); }
     else known = false;
   } else if (nm == "final_ln.weight") { SERENC_TRY(expect(d)); st = upload_f32(h->fin_g, data, n); }
@@ -1015,6 +1034,16 @@ struct StackBufs {
   float* gate = nullptr;  // [sumT, heads] WavLM gate of the current layer
 };
 
+// gate of layer li's attention, to be produced by the LayerNorm that writes its input (tcgen05 attention path only)
+LnGate ln_gate_for(const serenc_handle* h, const StackBufs& b, int li) {
+  LnGate g;
+  if (h->cfg.wavlm_rel_bias && h->head_dim == 64 && !h->force_mma_sync_attn && li < h->cfg.layers && b.gate) {
+    const LayerW& l = h->L[li];
+    g.w2 = l.gru_w2; g.b2 = l.gru_b2; g.gconst = l.gru_const; g.out = b.gate;
+  }
+  return g;
+}
+
 // Pre-LN ("stable layer norm") encoder stack + final LayerNorm, emitting the selected hidden states.
 // WavLMEncoderLayerStableLayerNorm / Wav2Vec2EncoderLayerStableLayerNorm / WhisperEncoderLayer
 // (HF modeling_wavlm.py:339-373, :450-522; modeling_whisper.py:361-414).
@@ -1025,7 +1054,8 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
   SERENC_TRY(emit_hidden(h, e, 0, b.x, st));
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = h->L[li];
-    SERENC_TRY((launch_ln_t<float, bf16, false>(h, b.x, d, b.hln, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
+    const LnGate lg = ln_gate_for(h, b, li);
+    SERENC_TRY((launch_ln_t<float, bf16, false>(h, b.x, d, b.hln, d, l.ln1_g, l.ln1_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, nullptr, lg)));
     {
       GemmCall g = linear_call(b.hln, sumT, d, l.w_qkv, 3 * d);
       g.bias = l.b_qkv; g.out_bf16 = b.qkv; g.ld_bf16 = 3 * d; g.prof_cls = SERENC_PROF_GEMM_QKV;
@@ -1036,6 +1066,7 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
       p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
+      p.gate_ready = lg.out != nullptr;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
     {
@@ -1072,7 +1103,7 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
                       double attn_flops, EmitCtx& e, cudaStream_t st) {
   const serenc_config& c = h->cfg;
   const int d = c.hidden;
-  SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln)));
+  SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln, ln_gate_for(h, b, 0))));
   SERENC_TRY(emit_hidden(h, e, 0, b.x, st));
   for (int li = 0; li < c.layers; ++li) {
     const LayerW& l = h->L[li];
@@ -1086,6 +1117,7 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
       p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
+      p.gate_ready = ln_gate_for(h, b, li).out != nullptr;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
     {
@@ -1104,7 +1136,7 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
       g.bias = l.b_fc2; g.resid = b.x; g.out_f32 = b.x; g.ld_f32 = d; g.prof_cls = SERENC_PROF_GEMM_FC2;
       SERENC_TRY(launch_gemm(h, g, st));
     }
-    SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln)));
+    SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln, ln_gate_for(h, b, li + 1))));
     SERENC_TRY(emit_hidden(h, e, li + 1, b.x, st));
   }
   if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
