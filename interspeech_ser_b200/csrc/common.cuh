@@ -292,8 +292,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of a CTA of this cluster. RELAXED: the callers only hand back TMEM accumulators, whose reads
+// are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync. (.release.cluster compiled to
+// MEMBAR.ALL.GPU, i.e. every epilogue warp drained its global stores before the accumulator could be reused:
+// ncu showed 0.67 membar-stalled warps per issue on the FC1 GEMM.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load into THIS CTA's shared memory, completion bytes credited to an mbarrier that may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
