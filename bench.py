@@ -109,6 +109,19 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: HF transformers fp32 on the host cores (what the reference scripts call)
 # --------------------------------------------------------------------------------------------------
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum averaged over the four GEMMs of one WavLM-large encoder layer).
+    A static, profiler-side number: null for workloads that were not captured."""
+    if workload != "wavlm-large":
+        return None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def cpu_reference_run(workload: str, steps: int, warmup: int, n_utts: int, max_seconds: float = 150.0):
     """One utterance per forward, as preprocess_speech.py:45-73 / preprocess_whisper.py:45-82 do."""
     import torch
@@ -315,7 +328,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all linear + implicit-GEMM conv launches of a step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": f"{peaks['source']} (bf16_tflops_sustained; burst {peaks['bf16_tflops']})",
+                         "traffic": ncu_traffic(args.workload), "peak_source": f"{peaks['source']} (bf16_tflops_sustained; burst {peaks['bf16_tflops']})",
                          "launches_per_step": gemm_n // prof_steps, "share_of_step": gemm_ms / total_prof_ms if total_prof_ms else None,
                          "algorithmic_gflop_per_step": gemm_fl / prof_steps / 1e9},
             "model_tflops": total_flops / (ms_total / args.steps / 1e3) / 1e12,
