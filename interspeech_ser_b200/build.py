@@ -18,7 +18,6 @@ LIB_PATH = os.path.join(PKG_DIR, "libserenc.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libserenc.stamp")
 
 SOURCES = ["serenc_api.cu"]
-HEADERS = ["common.cuh", "gemm_tcgen05.cuh", "attention.cuh", "attention_tc.cuh", "frontend_norm.cuh", "logmel.cuh"]
 
 
 def _nvcc() -> str:
@@ -30,7 +29,9 @@ def _nvcc() -> str:
 
 def _source_digest() -> str:
     hsh = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(REPO, "include", "serenc.h")]
+    # every file under csrc/ (a fixed header list once let edits to a new header go unbuilt)
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(REPO, "include", "serenc.h"))
     for f in files:
         with open(f, "rb") as fh:
             hsh.update(fh.read())
