@@ -43,6 +43,11 @@ WORKLOADS = {
                          "Whisper-large-v3 encoder: 128-bin log-mel frontend + encoder over 30 s synthetic audio, batch 32 per GPU (BASELINE configs[1])"),
     "hubert-xlarge": ("facebook/hubert-xlarge-ls960-ft", 8.0, 64, "HuBERT-xlarge-ls960 embedding extraction, 8 s utterances, batch 64 per GPU"),
     "xls-r-2b": ("facebook/wav2vec2-xls-r-2b", 8.0, 64, "wav2vec2-xls-r-2b embedding extraction, batch 64 x 8 s per GPU (BASELINE configs[3])"),
+    # corpus sweep in the style of BASELINE configs[4]: a step = the whole per-GPU corpus, length-sorted into packed
+    # batches by the scheduler (frame budget 28 416), one encode call per batch
+    "wavlm-large-sweep": ("microsoft/wavlm-large", None, 512,
+                          "WavLM-large (random-init) corpus sweep: 512 synthetic utterances per GPU, lengths U[2 s, 20 s], "
+                          "length-sorted packed batches from the scheduler (BASELINE configs[4] style)"),
 }
 
 
@@ -133,6 +138,8 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, n_utts: int, max_s
     cfg = configs.get_config(cfg_name)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if secs is None:
+        secs = 11.0   # corpus sweep: mean utterance length of U[2 s, 20 s]
     n = int(secs * 16000)
     waves = synth_batch(7, n_utts, n)
     kind = "reference"
@@ -219,27 +226,59 @@ def run_ours(args):
     if args.batch:
         batch = args.batch
     cfg = configs.get_config(cfg_name)
-    n = int(secs * 16000)
     weights = random_init(cfg, 0)
     model = (WhisperModel if cfg.family == "whisper" else SpeechEncoderModel)(cfg, weights, local_rank)
     del weights
     eng = model.engine
-
-    # every rank owns a different shard of the synthetic corpus (seed 7 = the scripts' default --seed)
-    host = torch.from_numpy(synth_batch(7 + 1000 * rank, batch, n)).pin_memory()
-    lens = [n] * batch
-    wav_dev = host.to(dev).reshape(-1).contiguous()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step_device():
-        return model.extract_device(wav_dev, lens, average=True, want_frames=False, want_pooled=True).pooled
+    if secs is None:
+        # corpus sweep: every rank owns its own synthetic corpus; the scheduler cuts it into packed batches
+        from interspeech_ser_b200 import scheduler
+        rng = np.random.default_rng(7 + 1000 * rank)
+        all_lens = [int(v) for v in rng.integers(2 * 16000, 20 * 16000 + 1, size=batch)]
+        plan = scheduler.make_batches(cfg, all_lens)
+        hosts, devs, blens = [], [], []
+        for bi, bt in enumerate(plan):
+            ls = [all_lens[i] for i in bt.indices]
+            hbuf = torch.from_numpy((rng.standard_normal(sum(ls), dtype=np.float32) * np.float32(WAVE_STD))).pin_memory()
+            hosts.append(hbuf); devs.append(hbuf.to(dev)); blens.append(ls)
+        secs_total = sum(all_lens) / 16000.0
+        h2d_bytes = sum(h.numel() * 4 for h in hosts)
+        pooled_hosts = [torch.empty((len(ls), cfg.hidden_size), dtype=torch.float32).pin_memory() for ls in blens]
 
-    pooled_host = torch.empty((batch, cfg.hidden_size), dtype=torch.float32).pin_memory()
+        def step_device():
+            out = None
+            for wv, ls in zip(devs, blens):
+                out = model.extract_device(wv, ls, average=True, want_frames=False, want_pooled=True).pooled
+            return out
 
-    def step_e2e():
-        w = host.to(dev, non_blocking=True).reshape(-1)
-        out = model.extract_device(w, lens, average=True, want_frames=False, want_pooled=True).pooled
-        pooled_host.copy_(out, non_blocking=True)
+        def step_e2e():
+            for hb, ls, ph in zip(hosts, blens, pooled_hosts):
+                out = model.extract_device(hb.to(dev, non_blocking=True), ls, average=True, want_frames=False, want_pooled=True).pooled
+                ph.copy_(out, non_blocking=True)
+
+        pooled_host = pooled_hosts[-1]
+        host = None
+        desc += f"; {len(plan)} batches, {sum(len(b) for b in blens)} utterances, {secs_total:.0f} audio-s per GPU and step"
+    else:
+        n = int(secs * 16000)
+        # every rank owns a different shard of the synthetic corpus (seed 7 = the scripts' default --seed)
+        host = torch.from_numpy(synth_batch(7 + 1000 * rank, batch, n)).pin_memory()
+        lens = [n] * batch
+        wav_dev = host.to(dev).reshape(-1).contiguous()
+        secs_total = batch * secs
+        h2d_bytes = host.numel() * 4
+
+        def step_device():
+            return model.extract_device(wav_dev, lens, average=True, want_frames=False, want_pooled=True).pooled
+
+        pooled_host = torch.empty((batch, cfg.hidden_size), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            w = host.to(dev, non_blocking=True).reshape(-1)
+            out = model.extract_device(w, lens, average=True, want_frames=False, want_pooled=True).pooled
+            pooled_host.copy_(out, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -282,7 +321,7 @@ def run_ours(args):
     ms_e2e, _ = timed(step_e2e, args.steps)
 
     # final host gather of the pooled embeddings (the path's only exchange)
-    if world > 1:
+    if world > 1 and secs is not None:
         gathered = [torch.empty_like(pooled_host, device=dev) for _ in range(world)] if rank == 0 else None
         dist.gather(pooled_host.to(dev), gathered, dst=0)
 
@@ -295,7 +334,7 @@ def run_ours(args):
     prof = eng.get_profile()
     eng.set_profiling(False)
 
-    audio_per_step = batch * secs * world
+    audio_per_step = secs_total * world
     value = audio_per_step * args.steps / (ms_total / 1e3)
     e2e_value = audio_per_step * args.steps / (ms_e2e / 1e3)
 
@@ -322,7 +361,7 @@ def run_ours(args):
                        "global_batch": batch * world, "output": "mean of last 4 hidden states -> masked-mean pooled [B, d] fp32",
                        "weights": "random init (seed 0)", "l2": "256 MiB buffer zeroed between timed steps (untimed)",
                        "parallelism": f"utterance-sharded replicas x{world}, no data-path collective"},
-            "e2e": {"value": e2e_value, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(batch * n * 4), "d2h_bytes_per_step": int(batch * cfg.hidden_size * 4),
+            "e2e": {"value": e2e_value, "unit": "audio-seconds/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(batch * cfg.hidden_size * 4),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
