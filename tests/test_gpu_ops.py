@@ -136,6 +136,43 @@ def _attn_ref(qkv, offs, H, bias_fn=None):
     return out
 
 
+def test_attention_wavlm_long_utterance():
+    """T = 1100 and 1500 frames (22 s / 30 s): relative positions beyond the 1023-entry Toeplitz table are clamped
+    (buckets saturate at |delta| >= 778, so the clamp is exact) and the bias window of a query tile outgrows the
+    4-CTA/SM shared-memory budget; next to a short utterance in the same packed batch."""
+    from interspeech_ser_b200.engine import Engine
+    from oracle import ssl_oracle as O
+    lib, dev = _lib.load_library(), torch.device("cuda:0")
+    cfg = configs.get_config("tiny/wavlm")
+    w = random_init(cfg, 0)
+    eng = Engine(cfg, w, 0)
+    d, H = cfg.hidden_size, cfg.num_attention_heads
+    g = torch.Generator().manual_seed(11)
+    lens = [1100, 37, 1500]
+    offs = [0]
+    for t in lens:
+        offs.append(offs[-1] + t)
+    R = offs[-1]
+    qkv = bf(torch.randn(R, 3 * d, generator=g))
+    hln = bf(torch.randn(R, d, generator=g))
+    scratch = torch.empty(4096, dtype=torch.uint8, device=dev)
+    out = torch.full((R, d), float("nan"), dtype=torch.bfloat16, device=dev)
+    li = 0
+
+    def bias_fn(s, e):
+        T = e - s
+        pb = O.wavlm_position_bias(cfg, w, T)
+        xh = hln[s:e].float().view(T, H, d // H).transpose(0, 1)
+        proj = torch.nn.functional.linear(xh, torch.from_numpy(w[f"layer{li}.gru.weight"]), torch.from_numpy(w[f"layer{li}.gru.bias"]))
+        gate = torch.sigmoid(proj.view(H, T, 2, 4).sum(-1))
+        gg = gate[..., 0] * (gate[..., 1] * torch.from_numpy(w[f"layer{li}.gru.const"]).view(H, 1) - 1.0) + 2.0
+        return gg[:, :, None] * pb
+    _lib.check(lib.serenc_op_attention(eng._h, qkv.to(dev).data_ptr(), _lib.i64_array(offs), len(lens), 1, li, hln.to(dev).data_ptr(),
+                                       out.data_ptr(), scratch.data_ptr(), stream(dev)))
+    torch.cuda.synchronize()
+    assert rel_err(out, _attn_ref(qkv, offs, H, bias_fn)) < 6e-3
+
+
 @pytest.mark.parametrize("name", ["tiny/wavlm", "tiny/wav2vec2", "tiny/hubert80", "tiny/w2v120"])
 def test_attention_varlen(name):
     """Packed variable-length attention (ragged: T = 1, 64, 65, 199, 333, 12), head_dim 64 / 80 / 120, and WavLM's gated
