@@ -17,6 +17,7 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc_wide.cuh"
 #include "common.cuh"
 #include "frontend_norm.cuh"
 #include "gemm_tcgen05.cuh"
@@ -219,6 +220,39 @@ int get_tmap(serenc_handle* h, const void* base, uint64_t cols, uint64_t rows, u
     SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p cols=%llu rows=%llu stride=%llu box=%u",
                 (int)r, base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes,
                 box_rows);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  h->tmaps[key] = *out;
+  return 0;
+}
+
+// rank-3 bf16 map over a packed [rows, 3 * heads * hd] q|k|v buffer seen as {hd, 3 * heads, rows}: box {64, 1, box_rows},
+// 128B swizzle. A box that starts at column 64 of a head runs past the head's extent and is zero-filled there.
+int get_tmap_heads(serenc_handle* h, const void* base, uint64_t hd, uint64_t slots, uint64_t rows, uint64_t row_stride_bytes,
+                   uint32_t box_rows, CUtensorMap* out) {
+  std::array<uint64_t, 8> key = {reinterpret_cast<uint64_t>(base), hd, rows, row_stride_bytes, box_rows, slots, 3, 0};
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (rows == 0) rows = 1;
+  cuuint64_t dims[3] = {hd, slots, rows};
+  cuuint64_t strides[2] = {hd * 2, row_stride_bytes};
+  cuuint32_t box[3] = {64, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled (rank 3) failed (%d): base=%p hd=%llu slots=%llu rows=%llu stride=%llu box=%u",
+                (int)r, base, (unsigned long long)hd, (unsigned long long)slots, (unsigned long long)rows,
+                (unsigned long long)row_stride_bytes, box_rows);
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->tmaps.size() > 4096) h->tmaps.clear();
   h->tmaps[key] = *out;
@@ -536,6 +570,21 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
+  if ((h->head_dim == 80 || h->head_dim == 120) && !wavlm && !h->force_mma_sync_attn) {
+    // tcgen05 path for wide heads: rank-3 {head_dim, 3 * heads, rows} maps (zero fill past the head's last column)
+    CUtensorMap tmq, tmkv;
+    AttnParams pt = p;
+    pt.heads = h->cfg.heads; pt.batch = batch;
+    SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
+    SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
+    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
+    if (h->head_dim == 80)
+      attention_tc_wide_kernel<80><<<grid, block, FawCfg<80>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+    else
+      attention_tc_wide_kernel<120><<<grid, block, FawCfg<120>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+    SERENC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (h->head_dim) {
     case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
     case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
@@ -767,6 +816,8 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));
   }
   if (st) {
     serenc_destroy(h);
@@ -1244,7 +1295,26 @@ struct Staging {
 };
 thread_local Staging g_stage;
 
-int stage_reserve(size_t bytes, void** out) {
+// `st` is the stream the staged bytes will be copied on. While that stream is being CAPTURED into a CUDA graph the
+// shared staging buffer must not be used: the copy node re-reads its host source at every replay, and the event
+// synchronisation below is illegal inside a capture. A captured call gets pinned memory of its own instead (kept for
+// the life of the process: a graph may be replayed at any time), and no event is recorded.
+std::mutex g_graph_stage_mu;
+std::vector<void*> g_graph_stage;   // pinned buffers owned by captured graphs
+thread_local bool g_stage_captured = false;
+
+int stage_reserve(size_t bytes, void** out, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  SERENC_CUDA_OK(cudaStreamIsCapturing(st, &cs));
+  g_stage_captured = (cs != cudaStreamCaptureStatusNone);
+  if (g_stage_captured) {
+    void* p = nullptr;
+    SERENC_CUDA_OK(cudaMallocHost(&p, bytes ? bytes : 1));   // needs a relaxed / thread-local capture mode on the caller's side
+    std::lock_guard<std::mutex> lk(g_graph_stage_mu);
+    g_graph_stage.push_back(p);
+    *out = p;
+    return 0;
+  }
   Staging& s = g_stage;
   if (s.pending) { SERENC_CUDA_OK(cudaEventSynchronize(s.ev)); s.pending = false; }
   if (bytes > s.cap) {
@@ -1259,6 +1329,7 @@ int stage_reserve(size_t bytes, void** out) {
   return 0;
 }
 int stage_commit(cudaStream_t st) {
+  if (g_stage_captured) return 0;
   SERENC_CUDA_OK(cudaEventRecord(g_stage.ev, st));
   g_stage.pending = true;
   return 0;
@@ -1267,7 +1338,7 @@ int stage_commit(cudaStream_t st) {
 // stage a [batch] UttSpan table (sample ranges only) and copy it to `dst_dev`
 int upload_spans(const int64_t* sample_start, const int32_t* sample_len, int batch, UttSpan* dst_dev, cudaStream_t st) {
   void* hs;
-  SERENC_TRY(stage_reserve(sizeof(UttSpan) * (size_t)batch, &hs));
+  SERENC_TRY(stage_reserve(sizeof(UttSpan) * (size_t)batch, &hs, st));
   UttSpan* hu = reinterpret_cast<UttSpan*>(hs);
   for (int b = 0; b < batch; ++b) {
     hu[b].sample_start = sample_start[b];
@@ -1336,7 +1407,7 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   {
     const size_t sz_u = sizeof(Conv0Utt) * batch, sz_f = 4 * (size_t)(batch + 1), sz_r = 4 * (size_t)batch;
     void* hs;
-    SERENC_TRY(stage_reserve(sz_u + sz_f + sz_r + 64, &hs));
+    SERENC_TRY(stage_reserve(sz_u + sz_f + sz_r + 64, &hs, st));
     Conv0Utt* hu = reinterpret_cast<Conv0Utt*>(hs);
     for (int b = 0; b < batch; ++b) {
       hu[b].sample_start = sample_start[b];
@@ -1462,7 +1533,7 @@ extern "C" int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, c
   int32_t* d_off;
   SERENC_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_off), 4 * (size_t)(batch + 1), st));
   void* hs;
-  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs));
+  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs, st));
   for (int b = 0; b <= batch; ++b) reinterpret_cast<int32_t*>(hs)[b] = (int32_t)frame_offsets[b];
   SERENC_CUDA_OK(cudaMemcpyAsync(d_off, hs, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
   SERENC_TRY(stage_commit(st));
@@ -1553,7 +1624,7 @@ extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int
 
   {
     void* hs;
-    SERENC_TRY(stage_reserve(4 * (size_t)(2 * batch + 1), &hs));
+    SERENC_TRY(stage_reserve(4 * (size_t)(2 * batch + 1), &hs, st));
     int32_t* hf = reinterpret_cast<int32_t*>(hs);
     for (int b = 0; b <= batch; ++b) hf[b] = b * 1500;
     for (int b = 0; b < batch; ++b) hf[batch + 1 + b] = n_keep ? (n_keep[b] < 1 ? 1 : (n_keep[b] > 1500 ? 1500 : n_keep[b])) : 1500;
@@ -1670,7 +1741,7 @@ extern "C" int serenc_op_attention(serenc_handle* h, const void* qkv, const int6
   const int d = h->cfg.hidden;
   int32_t* d_off = reinterpret_cast<int32_t*>(scratch_dev);
   void* hs;
-  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs));
+  SERENC_TRY(stage_reserve(4 * (size_t)(batch + 1), &hs, st));
   int tmax = 0;
   for (int b = 0; b <= batch; ++b) {
     reinterpret_cast<int32_t*>(hs)[b] = (int32_t)frame_offsets[b];
