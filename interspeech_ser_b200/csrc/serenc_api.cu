@@ -112,6 +112,7 @@ struct serenc_handle {
   bool no_posconv_slab = false;   // SERENC_NO_POSCONV_SLAB=1: positional conv through the generic implicit GEMM
   int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
   bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: head_dim-64 attention on the mma.sync kernel
+  int attn_deep64 = 0;               // SERENC_ATTN_DEEP64=1: bias-free head_dim-64 attention on the deep-pipelined kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
 };
@@ -544,7 +545,7 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
                 cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
   ProfScope ps(h, SERENC_PROF_ATTENTION, 1, alg_flops, 0.0, st);
-  if (h->head_dim == 64 && !h->force_mma_sync_attn) {
+  if (h->head_dim == 64 && !h->force_mma_sync_attn && (wavlm || !h->attn_deep64)) {
     // tcgen05 path: Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
     CUtensorMap tmq, tmkv;
     AttnParams pt = p;
@@ -570,16 +571,19 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  if ((h->head_dim == 80 || h->head_dim == 120) && !wavlm && !h->force_mma_sync_attn) {
+  if ((h->head_dim == 80 || h->head_dim == 120 || h->head_dim == 64) && !wavlm && !h->force_mma_sync_attn) {
     // tcgen05 path for wide heads: rank-3 {head_dim, 3 * heads, rows} maps (zero fill past the head's last column)
     CUtensorMap tmq, tmkv;
     AttnParams pt = p;
+    pt.trace = h->gemm_trace;
     pt.heads = h->cfg.heads; pt.batch = batch;
     SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
     SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
     const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
     if (h->head_dim == 80)
       attention_tc_wide_kernel<80><<<grid, block, FawCfg<80>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+    else if (h->head_dim == 64)
+      attention_tc_wide_kernel<64><<<grid, block, FawCfg<64>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
     else
       attention_tc_wide_kernel<120><<<grid, block, FawCfg<120>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
     SERENC_CUDA_OK(cudaGetLastError());
@@ -762,6 +766,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_ATTN_DEEP64"); if (e) h->attn_deep64 = e[0] == '1'; }
   *out = h;
 
   int st = 0;
@@ -816,6 +821,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));
   }

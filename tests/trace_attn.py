@@ -1,4 +1,5 @@
-"""Dev tool: per-CTA clock stamps of the tcgen05 attention kernel (WavLM-large shape: 142 x 16 heads x T=199)."""
+"""Dev tool: per-CTA clock stamps of the tcgen05 attention kernels (default WavLM-large shape: 142 x 16 heads x T=199;
+MODEL=facebook/hubert-xlarge-ls960-ft B=64 T=399 for the wide-head kernel)."""
 import os, sys
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +8,7 @@ from interspeech_ser_b200 import _lib, configs
 from interspeech_ser_b200.engine import Engine
 from interspeech_ser_b200.weights import random_init
 dev = torch.device("cuda:0")
-cfg = configs.get_config("microsoft/wavlm-large")
+cfg = configs.get_config(os.environ.get("MODEL", "microsoft/wavlm-large"))
 import dataclasses
 cfg = dataclasses.replace(cfg, num_hidden_layers=1)
 eng = Engine(cfg, random_init(cfg, 0), 0)
@@ -22,7 +23,7 @@ hln = (torch.randn(R, d, device=dev)).to(torch.bfloat16)
 out = torch.empty(R, d, device=dev, dtype=torch.bfloat16)
 scratch = torch.empty(1 << 16, dtype=torch.uint8, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for wavlm in (1, 0):
+for wavlm in ((1, 0) if cfg.family == "wavlm" else (0,)):
     def run():
         _lib.check(lib.serenc_op_attention(eng._h, qkv.data_ptr(), _lib.i64_array(offs), B, wavlm, 0, hln.data_ptr() if wavlm else None, out.data_ptr(), scratch.data_ptr(), st))
     for _ in range(3):
