@@ -23,6 +23,7 @@
 #pragma once
 #include "attention.cuh"
 #include "common.cuh"
+#include <type_traits>
 
 namespace serenc {
 
@@ -311,20 +312,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);
             tmem_ld_wait();
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (WAVLM) {   // x = s * scale * log2e + gate * bias, two keys per FMUL2 / FFMA2
+              const uint64_t sc22 = pack_f32x2(sc2, sc2), gate2 = pack_f32x2(gate, gate);
+              const float* wk = win + j0 + c * 32;
+#pragma unroll
+              for (int k = 0; k < 32; k += 2) {
+                const uint64_t x2 = ffma2(gate2, pack_f32x2(wk[k], wk[k + 1]),
+                                          fmul2(pack_f32x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), sc22));
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                r[k] = __float_as_uint(x0);
+                r[k + 1] = __float_as_uint(x1);
+              }
+            }
             if (full) {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                float x = __uint_as_float(r[k]);
-                if (WAVLM) { x = fmaf(gate, win[j0 + c * 32 + k], x * sc2); r[k] = __float_as_uint(x); }
-                m4[k & 3] = fmaxf(m4[k & 3], x);
-              }
+              for (int k = 0; k < 32; ++k) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(r[k]));
             } else {
 #pragma unroll
-              for (int k = 0; k < 32; ++k) {
-                float x = __uint_as_float(r[k]);
-                if (WAVLM) { x = fmaf(gate, win[j0 + c * 32 + k], x * sc2); r[k] = __float_as_uint(x); }
-                if (c * 32 + k < ncols) m4[k & 3] = fmaxf(m4[k & 3], x);
-              }
+              for (int k = 0; k < 32; ++k)
+                if (c * 32 + k < ncols) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(r[k]));
             }
             if (WAVLM) tmem_st_32x32b_x32(t_lane + FA_TMEM_S + c * 32, r);   // pass 2 reads x back instead of redoing the bias
             mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
@@ -361,44 +368,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float rs = 0.f;
       const bool two = FA_BN / 2 < ncols;   // CTA-uniform: the second 32-column chunk holds valid keys
       const float neg_m = -m_new;
-      auto chunk = [&](uint32_t (&r)[32], const int c) {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+      // FULLC (compile-time) = every key of the block is valid: no per-element masking in the hot path
+      const uint64_t negm2 = pack_f32x2(neg_m, neg_m), sc22 = pack_f32x2(sc2, sc2);
+      auto chunk = [&](uint32_t (&r)[32], const int c, auto fullc) {
+        constexpr bool FULLC = decltype(fullc)::value;
+        uint64_t acc0 = 0ull, acc1 = 0ull;   // packed fp32 partial sums (bit pattern 0 = +0.0f, +0.0f)
+        uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float x = __uint_as_float(r[k]);
-          float e;
-          if (WAVLM) e = fast_exp2(x + neg_m);
-          else e = fast_exp2(fmaf(x, sc2, neg_m));
-          if (!full && c * 32 + k >= ncols) e = 0.f;
-          s4[k & 3] += e;
-          r[k] = __float_as_uint(e);
+        for (int k = 0; k < 32; k += 2) {
+          const uint64_t s2 = pack_f32x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1]));
+          const uint64_t x2 = WAVLM ? fadd2(s2, negm2) : ffma2(s2, sc22, negm2);
+          float x0, x1;
+          unpack_f32x2(x2, x0, x1);
+          float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          if (!FULLC) {
+            if (c * 32 + k >= ncols) e0 = 0.f;
+            if (c * 32 + k + 1 >= ncols) e1 = 0.f;
+          }
+          const uint64_t e2 = pack_f32x2(e0, e1);
+          if (k & 2) acc1 = fadd2(acc1, e2); else acc0 = fadd2(acc0, e2);
+          pk[k >> 1] = pack_bf16x2(e0, e1);
         }
-        rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        float a0, a1, a2, a3;
+        unpack_f32x2(acc0, a0, a1);
+        unpack_f32x2(acc1, a2, a3);
+        rs += (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int k8 = 0; k8 < 4; ++k8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]), __uint_as_float(r[k8 * 8 + 1]));
-          u.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]), __uint_as_float(r[k8 * 8 + 3]));
-          u.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]), __uint_as_float(r[k8 * 8 + 5]));
-          u.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]), __uint_as_float(r[k8 * 8 + 7]));
           const int ch = c * 4 + k8;
-          *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = u;
+          *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) =
+              make_uint4(pk[k8 * 4 + 0], pk[k8 * 4 + 1], pk[k8 * 4 + 2], pk[k8 * 4 + 3]);
         }
       };
       if (warp_valid) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_lane + FA_TMEM_S, r);
         tmem_ld_wait();
-        chunk(r, 0);
-        if (two) {
+        if (full) {
+          chunk(r, 0, std::true_type{});
           tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + 32, r);
           tmem_ld_wait();
-          chunk(r, 1);
+          chunk(r, 1, std::true_type{});
         } else {
+          chunk(r, 0, std::false_type{});
+          if (two) {
+            tmem_ld_32x32b_x32(t_lane + FA_TMEM_S + 32, r);
+            tmem_ld_wait();
+            chunk(r, 1, std::false_type{});
+          } else {
 #pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const int ch = 4 + k8;
-            *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            for (int k8 = 0; k8 < 4; ++k8) {
+              const int ch = 4 + k8;
+              *reinterpret_cast<uint4*>(sP + row * 128 + ((ch ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
         }
       }

@@ -276,33 +276,49 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       float rs = 0.f;
       const bool two = FA_BN / 2 < ncols;   // CTA-uniform
       const float neg_m = -m_new;
-      auto chunk = [&](const int c) {
+      // FULLC (compile-time) = every key of the block is valid: no per-element masking in the hot path
+      const uint64_t negm2 = pack_f32x2(neg_m, neg_m), sc22 = pack_f32x2(sc2, sc2);
+      auto chunk = [&](const int c, auto fullc) {
+        constexpr bool FULLC = decltype(fullc)::value;
         uint32_t r[32];
         tmem_ld_32x32b_x32(t_s + c * 32, r);
         tmem_ld_wait();
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float e = fast_exp2(fmaf(__uint_as_float(r[k]), sc2, neg_m));
-          if (!full && c * 32 + k >= ncols) e = 0.f;
-          s4[k & 3] += e;
-          r[k] = __float_as_uint(e);
-        }
-        rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        uint64_t acc0 = 0ull, acc1 = 0ull;   // packed fp32 partial sums (bit pattern 0 = +0.0f, +0.0f)
         uint32_t pk[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+        for (int k = 0; k < 32; k += 2) {
+          const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), sc22, negm2);
+          float x0, x1;
+          unpack_f32x2(x2, x0, x1);
+          float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          if (!FULLC) {
+            if (c * 32 + k >= ncols) e0 = 0.f;
+            if (c * 32 + k + 1 >= ncols) e1 = 0.f;
+          }
+          const uint64_t e2 = pack_f32x2(e0, e1);
+          if (k & 2) acc1 = fadd2(acc1, e2); else acc0 = fadd2(acc0, e2);
+          pk[k >> 1] = pack_bf16x2(e0, e1);
+        }
+        float a0, a1, a2, a3;
+        unpack_f32x2(acc0, a0, a1);
+        unpack_f32x2(acc1, a2, a3);
+        rs += (a0 + a1) + (a2 + a3);
         tmem_st_32x32b_x16(t_s + c * 16, pk);   // chunk 1 lands on S columns [16, 32): consumed by chunk 0 already
       };
       if (warp_valid) {
-        chunk(0);
-        if (two) {
-          chunk(1);
+        if (full) {
+          chunk(0, std::true_type{});
+          chunk(1, std::true_type{});
         } else {
-          uint32_t z[16];
+          chunk(0, std::false_type{});
+          if (two) {
+            chunk(1, std::false_type{});
+          } else {
+            uint32_t z[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) z[k] = 0u;
-          tmem_st_32x32b_x16(t_s + 16, z);
+            for (int k = 0; k < 16; ++k) z[k] = 0u;
+            tmem_st_32x32b_x16(t_s + 16, z);
+          }
         }
       }
       l_run = l_run * alpha + rs;
