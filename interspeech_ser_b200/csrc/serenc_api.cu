@@ -111,7 +111,7 @@ struct serenc_handle {
   bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
   bool no_posconv_slab = false;   // SERENC_NO_POSCONV_SLAB=1: positional conv through the generic implicit GEMM
   int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
-  bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: head_dim-64 attention on the mma.sync kernel
+  bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: attention on the mma.sync kernel (A/B arm)
   int attn_deep64 = 0;               // SERENC_ATTN_DEEP64=1: bias-free head_dim-64 attention on the deep-pipelined kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
@@ -700,7 +700,7 @@ extern "C" int serenc_wavlm_bucket(int delta, int num_buckets, int max_distance)
 }
 
 extern "C" const char* serenc_last_error(void) { return g_err; }
-extern "C" const char* serenc_version(void) { return "serenc 0.1 (sm_100a; tcgen05 GEMM, mma.sync attention)"; }
+extern "C" const char* serenc_version(void) { return "serenc 0.1 (sm_100a; tcgen05 GEMM + attention)"; }
 
 extern "C" int serenc_debug_gemm_trace(serenc_handle* h, void* dev_buf) {
   if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
@@ -1303,10 +1303,11 @@ thread_local Staging g_stage;
 
 // `st` is the stream the staged bytes will be copied on. While that stream is being CAPTURED into a CUDA graph the
 // shared staging buffer must not be used: the copy node re-reads its host source at every replay, and the event
-// synchronisation below is illegal inside a capture. A captured call gets pinned memory of its own instead (kept for
-// the life of the process: a graph may be replayed at any time), and no event is recorded.
+// synchronisation below is illegal inside a capture. A captured call gets host memory of its own instead (plain
+// malloc: cudaMallocHost is itself prohibited under the default capture mode; kept for the life of the process
+// because a graph may be replayed at any time), and no event is recorded.
 std::mutex g_graph_stage_mu;
-std::vector<void*> g_graph_stage;   // pinned buffers owned by captured graphs
+std::vector<void*> g_graph_stage;   // host buffers owned by captured graphs
 thread_local bool g_stage_captured = false;
 
 int stage_reserve(size_t bytes, void** out, cudaStream_t st) {
@@ -1314,8 +1315,8 @@ int stage_reserve(size_t bytes, void** out, cudaStream_t st) {
   SERENC_CUDA_OK(cudaStreamIsCapturing(st, &cs));
   g_stage_captured = (cs != cudaStreamCaptureStatusNone);
   if (g_stage_captured) {
-    void* p = nullptr;
-    SERENC_CUDA_OK(cudaMallocHost(&p, bytes ? bytes : 1));   // needs a relaxed / thread-local capture mode on the caller's side
+    void* p = malloc(bytes ? bytes : 1);
+    if (!p) SERENC_FAIL(SERENC_ERR_CUDA, "out of host memory staging %zu bytes for a captured call", bytes);
     std::lock_guard<std::mutex> lk(g_graph_stage_mu);
     g_graph_stage.push_back(p);
     *out = p;

@@ -125,6 +125,31 @@ def test_baseline_config0_batching_invariance_and_determinism():
     assert a.shape == (8, 1024) and torch.isfinite(a).all()
 
 
+def test_encode_call_is_cuda_graph_capturable():
+    """SURVEY 8b ownership row: no hidden allocation or synchronisation on the call path, so one encode call through
+    the C ABI (span upload, every kernel, pooling) can be captured into a CUDA graph and replayed on new waveform
+    contents in the same buffers; the replay must equal the eager call bit for bit."""
+    cfg, w, model = get_model("microsoft/wavlm-large")
+    lens = [64000] * 8
+    wa = torch.from_numpy(np.concatenate([synth_wave(200 + j, 64000) for j in range(8)]))
+    wb = torch.from_numpy(np.concatenate([synth_wave(300 + j, 64000) for j in range(8)]))
+    static = torch.empty(8 * 64000, dtype=torch.float32, device=model.device)
+    static.copy_(wa)
+    eager_a = model.extract_device(static, lens, average=True).pooled.clone()   # also sizes the workspace outside the capture
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = model.extract_device(static, lens, average=True).pooled
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager_a)
+    static.copy_(wb)
+    g.replay()
+    torch.cuda.synchronize()
+    got_b = out.clone()
+    eager_b = model.extract_device(static, lens, average=True).pooled
+    assert torch.equal(got_b, eager_b) and not torch.equal(got_b, eager_a)
+
+
 def test_lora_checkpoint_merged_at_load(tmp_path):
     """preprocess_speech_pretrained.py:120-178: a peft LoRA (r=8, alpha=16, q_proj/v_proj) classifier state dict,
     loaded from its .pt file, must give the embeddings of base + adapter (oracle run on independently merged weights)."""
