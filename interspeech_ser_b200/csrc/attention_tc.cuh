@@ -166,10 +166,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
       fence_mbar_init();
+      // the first Q / K / V tiles are requested before the TMEM allocation and the setup barrier: their ~2 000-cycle
+      // round trip is the longest item of a CTA's prologue
+      mbar_arrive_expect_tx(bar_q, FA_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, bar_q, h * FA_HD, r0 + i0);
+      mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
+      tma_load_2d(sK, &tmKV, bar_k, p.d + h * FA_HD, r0);
+      mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
+      tma_load_2d(sV, &tmKV, bar_v, 2 * p.d + h * FA_HD, r0);
     }
     __syncwarp();
     tmem_alloc(tmem_slot, FA_TMEM_COLS);
     tmem_relinquish();
+  } else if (WAVLM) {
+    // bias window of this query tile: wbuf[x] = bias_h[x - 127 - i0]; row r later reads win[key] = wbuf[key + 127 - r].
+    // Filled here, four independent L2 loads in flight per thread, so that it sits under the TMEM allocation and the
+    // Q / K loads (as a dependent loop after the setup barrier it cost ~2 300 cycles of every CTA); the setup barrier
+    // below publishes it.
+    const float* btab_h = p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1);
+    const int nwin = FA_BM - 1 + FA_BN * nkv;
+    for (int x0 = tid; x0 < nwin; x0 += 4 * 128) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int dlt = x0 + u * 128 - (FA_BM - 1) - i0;
+        dlt = max(-(WAVLM_MAXD - 1), min(WAVLM_MAXD - 1, dlt));   // buckets saturate at |delta| >= 778
+        v[u] = __ldg(btab_h + dlt);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (x0 + u * 128 < nwin) s_win[x0 + u * 128] = v[u];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -193,15 +220,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint64_t kdesc = umma_desc_sw128(smem_u32(sK));
       const uint64_t pdesc = umma_desc_sw128(smem_u32(sP));
       const uint64_t vdesc = umma_desc_sw128_mn(smem_u32(sV));
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar_q, FA_Q_BYTES);
-        tma_load_2d(sQ, &tmQ, bar_q, colq, r0u + i0);
-        mbar_arrive_expect_tx(bar_k, FA_KV_BYTES);
-        tma_load_2d(sK, &tmKV, bar_k, colk, r0u);
-        mbar_arrive_expect_tx(bar_v, FA_KV_BYTES);
-        tma_load_2d(sV, &tmKV, bar_v, colv, r0u);
-      }
-      __syncwarp();
       mbar_wait(bar_q, 0);
       fa_stamp(tr, 2);
       mbar_wait(bar_k, 0);
@@ -276,19 +294,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float gate = 0.f;
     const float* win = nullptr;
     if (WAVLM) {
-      // gate[row, head] comes precomputed (wavlm_gate_kernel); the bias window of this query tile is loaded once:
-      // wbuf[x] = bias_h[x - 127 - i0], and row r reads win[key] = wbuf[key + 127 - r]. Both sit under the Q/K/V loads.
+      // gate[row, head] comes precomputed (LayerNorm epilogue or wavlm_gate_kernel); the bias window was filled before
+      // the setup barrier
       if (row_valid) gate = __ldg(p.gate + (int64_t)(r0 + qi) * p.heads + h);
-      const float* btab_h = p.btab + (int64_t)h * (2 * WAVLM_MAXD - 1) + (WAVLM_MAXD - 1);
-      const int nwin = FA_BM - 1 + FA_BN * nkv;
-      for (int x = tid; x < nwin; x += 128) {
-        int dlt = x - (FA_BM - 1) - i0;
-        dlt = max(-(WAVLM_MAXD - 1), min(WAVLM_MAXD - 1, dlt));   // buckets saturate at |delta| >= 778
-        s_win[x] = __ldg(btab_h + dlt);
-      }
       win = s_win + (FA_BM - 1 - row);
       gate *= LOG2E;
-      softmax_group_sync();
     }
     fa_stamp(tr, 2);
     float m_run = -INFINITY, l_run = 0.f;

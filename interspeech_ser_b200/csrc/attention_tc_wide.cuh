@@ -109,6 +109,27 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(bar_p, 128);
       mbar_init(bar_o, 1);
       fence_mbar_init();
+      // first tiles requested before the TMEM allocation and the setup barrier (the longest item of the prologue)
+      const int slot_q = h, slot_k = p.heads + h, slot_v = 2 * p.heads + h;
+      mbar_arrive_expect_tx(bar_q, C::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < C::NCH; ++c) tma_load_3d(sQ + c * C::Q_CHUNK, &tmQ, bar_q, c * 64, slot_q, r0 + i0);
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (s2 < nkv) {
+          mbar_arrive_expect_tx(bar_k + s2, C::KV_BYTES);
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) tma_load_3d(sK + s2 * C::KV_BYTES + c * C::KV_CHUNK, &tmKV, bar_k + s2, c * 64, slot_k, r0 + s2 * FA_BN);
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (s2 < nkv) {
+          mbar_arrive_expect_tx(bar_v + s2, C::KV_BYTES);
+#pragma unroll
+          for (int c = 0; c < C::NCH; ++c) tma_load_3d(sV + s2 * C::KV_BYTES + c * C::KV_CHUNK, &tmKV, bar_v + s2, c * 64, slot_v, r0 + s2 * FA_BN);
+        }
+      }
     }
     __syncwarp();
     tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -146,16 +167,6 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       umma_commit(bar_s + (i & 1));
     };
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(bar_q, C::Q_BYTES);
-#pragma unroll
-      for (int c = 0; c < C::NCH; ++c) tma_load_3d(sQ + c * C::Q_CHUNK, &tmQ, bar_q, c * 64, slot_q, r0u + i0);
-      load_kv(sK, bar_k, slot_k, 0);
-      if (nk > 1) load_kv(sK + C::KV_BYTES, bar_k + 1, slot_k, FA_BN);
-      load_kv(sV, bar_v, slot_v, 0);
-      if (nk > 1) load_kv(sV + C::KV_BYTES, bar_v + 1, slot_v, FA_BN);
-    }
-    __syncwarp();
     mbar_wait(bar_q, 0);
     fa_stamp(tr, 2);
     mbar_wait(bar_k, 0);
