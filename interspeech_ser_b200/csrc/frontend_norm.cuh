@@ -137,14 +137,14 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__
   }
   __syncthreads();
 
-  float wr[16][CONV0_K];
+  // Channel pairs (64 i + 2 lane, + 1) are carried as packed fp32x2 values: the 160 FMAs of a frame issue as 80
+  // FFMA2, and the LayerNorm / GELU arithmetic as FADD2 / FMUL2 / FFMA2 (per-lane IEEE results, half the issue slots).
+  uint64_t wr[8][CONV0_K];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
 #pragma unroll
-    for (int j = 0; j < CONV0_K; ++j) {
-      wr[2 * i][j] = ws[(64 * i + 2 * lane) * CONV0_K + j];
-      wr[2 * i + 1][j] = ws[(64 * i + 2 * lane + 1) * CONV0_K + j];
-    }
+    for (int j = 0; j < CONV0_K; ++j)
+      wr[i][j] = pack_f32x2(ws[(64 * i + 2 * lane) * CONV0_K + j], ws[(64 * i + 2 * lane + 1) * CONV0_K + j]);
   }
 
   const int t_end = min(CONV0_TILE, u.slot - t0);
@@ -161,24 +161,28 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__
       }
       continue;
     }
-    float a[16];
+    uint64_t a[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float2 b = s_b[32 * i + lane];
-      a[2 * i] = b.x;
-      a[2 * i + 1] = b.y;
+      a[i] = pack_f32x2(b.x, b.y);
     }
 #pragma unroll
     for (int j = 0; j < CONV0_K; ++j) {
       const float xv = xs[f * CONV0_S + j];
+      const uint64_t xv2 = pack_f32x2(xv, xv);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) a[i] = fmaf(wr[i][j], xv, a[i]);
+      for (int i = 0; i < 8; ++i) a[i] = ffma2(wr[i][j], xv2, a[i]);
     }
     if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        gsum[i] += a[i];
-        gsq[i] = fmaf(a[i], a[i], gsq[i]);
+      for (int i = 0; i < 8; ++i) {
+        float a0, a1;
+        unpack_f32x2(a[i], a0, a1);
+        gsum[2 * i] += a0;
+        gsum[2 * i + 1] += a1;
+        gsq[2 * i] = fmaf(a0, a0, gsq[2 * i]);
+        gsq[2 * i + 1] = fmaf(a1, a1, gsq[2 * i + 1]);
       }
       continue;
     }
@@ -186,26 +190,34 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
-        orow[32 * i + lane] = pack_bf16x2(gelu_erf_fast(fmaf(a[2 * i], g.x, be.x)), gelu_erf_fast(fmaf(a[2 * i + 1], g.y, be.y)));
+        float v0, v1, y0, y1;
+        unpack_f32x2(ffma2(a[i], pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), v0, v1);
+        gelu_erf_fast2(v0, v1, y0, y1);
+        orow[32 * i + lane] = pack_bf16x2(y0, y1);
       }
       continue;
     }
-    float s = 0.f;
+    uint64_t s2 = fadd2(fadd2(fadd2(a[0], a[1]), fadd2(a[2], a[3])), fadd2(fadd2(a[4], a[5]), fadd2(a[6], a[7])));
+    float s_lo, s_hi;
+    unpack_f32x2(s2, s_lo, s_hi);
+    const float mu = warp_sum(s_lo + s_hi) * (1.f / CONV0_C);
+    const uint64_t nmu2 = pack_f32x2(-mu, -mu);
+    uint64_t q2 = 0ull;   // (+0.0f, +0.0f)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) s += a[i];
-    const float mu = warp_sum(s) * (1.f / CONV0_C);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float d = a[i] - mu;
-      q += d * d;
+    for (int i = 0; i < 8; ++i) {
+      a[i] = fadd2(a[i], nmu2);          // centred values, reused below
+      q2 = ffma2(a[i], a[i], q2);
     }
-    const float rs = rsqrtf(warp_sum(q) * (1.f / CONV0_C) + 1e-5f);
+    float q_lo, q_hi;
+    unpack_f32x2(q2, q_lo, q_hi);
+    const float rs = rsqrtf(warp_sum(q_lo + q_hi) * (1.f / CONV0_C) + 1e-5f);
+    const uint64_t rs2 = pack_f32x2(rs, rs);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
-      const float y0 = gelu_erf_fast((a[2 * i] - mu) * rs * g.x + be.x);
-      const float y1 = gelu_erf_fast((a[2 * i + 1] - mu) * rs * g.y + be.y);
+      float v0, v1, y0, y1;
+      unpack_f32x2(ffma2(fmul2(a[i], rs2), pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), v0, v1);
+      gelu_erf_fast2(v0, v1, y0, y1);
       orow[32 * i + lane] = pack_bf16x2(y0, y1);
     }
   }
@@ -381,7 +393,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
       o.z = (v[r][i].z - mu[r]) * rs[r] * g.z + be.z;
       o.w = (v[r][i].w - mu[r]) * rs[r] * g.w + be.w;
       if (GELU) {
-        o.x = gelu_erf_fast(o.x); o.y = gelu_erf_fast(o.y); o.z = gelu_erf_fast(o.z); o.w = gelu_erf_fast(o.w);
+        gelu_erf_fast2(o.x, o.y, o.x, o.y);
+        gelu_erf_fast2(o.z, o.w, o.z, o.w);
       }
       store4<TOut>(out + orow[r] * ld_out + c, o);
       if (out2) store4<bf16>(out2 + orow[r] * ld_out2 + c, o);
