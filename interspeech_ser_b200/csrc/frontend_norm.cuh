@@ -364,17 +364,24 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
   float mu[RPW], rs[RPW];
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
-    float s = 0.f;
+    // packed fp32x2 arithmetic (FADD2 / FFMA2): same two-pass statistics, half the issue slots
+    uint64_t s2 = 0ull;   // (+0.0f, +0.0f)
 #pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
-    mu[r] = warp_sum(s) * invC;
-    float q = 0.f;
+    for (int i = 0; i < NV; ++i) s2 = fadd2(s2, fadd2(pack_f32x2(v[r][i].x, v[r][i].y), pack_f32x2(v[r][i].z, v[r][i].w)));
+    float s_lo, s_hi;
+    unpack_f32x2(s2, s_lo, s_hi);
+    mu[r] = warp_sum(s_lo + s_hi) * invC;
+    const uint64_t nmu2 = pack_f32x2(-mu[r], -mu[r]);
+    uint64_t q2 = 0ull;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float a = v[r][i].x - mu[r], b = v[r][i].y - mu[r], c = v[r][i].z - mu[r], d = v[r][i].w - mu[r];
-      q += (a * a + b * b) + (c * c + d * d);
+      const uint64_t ab = fadd2(pack_f32x2(v[r][i].x, v[r][i].y), nmu2), cd = fadd2(pack_f32x2(v[r][i].z, v[r][i].w), nmu2);
+      q2 = ffma2(ab, ab, q2);
+      q2 = ffma2(cd, cd, q2);
     }
-    rs[r] = rsqrtf(warp_sum(q) * invC + eps);
+    float q_lo, q_hi;
+    unpack_f32x2(q2, q_lo, q_hi);
+    rs[r] = rsqrtf(warp_sum(q_lo + q_hi) * invC + eps);
   }
   // gate partials: after the first exchange (xor 8) lanes with bit 3 clear carry a_i, lanes with bit 3 set b_i
   float gu[RPW][NV <= 8 ? NV : 1];
@@ -388,10 +395,9 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
     for (int r = 0; r < RPW; ++r) {
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (orow[r] >= 0) {
-      o.x = (v[r][i].x - mu[r]) * rs[r] * g.x + be.x;
-      o.y = (v[r][i].y - mu[r]) * rs[r] * g.y + be.y;
-      o.z = (v[r][i].z - mu[r]) * rs[r] * g.z + be.z;
-      o.w = (v[r][i].w - mu[r]) * rs[r] * g.w + be.w;
+      const uint64_t nmu2 = pack_f32x2(-mu[r], -mu[r]), rs2 = pack_f32x2(rs[r], rs[r]);
+      unpack_f32x2(ffma2(fmul2(fadd2(pack_f32x2(v[r][i].x, v[r][i].y), nmu2), rs2), pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), o.x, o.y);
+      unpack_f32x2(ffma2(fmul2(fadd2(pack_f32x2(v[r][i].z, v[r][i].w), nmu2), rs2), pack_f32x2(g.z, g.w), pack_f32x2(be.z, be.w)), o.z, o.w);
       if (GELU) {
         gelu_erf_fast2(o.x, o.y, o.x, o.y);
         gelu_erf_fast2(o.z, o.w, o.z, o.w);
