@@ -35,6 +35,9 @@ def build_parser(whisper: bool) -> argparse.ArgumentParser:
     p.add_argument("--random_init", action="store_true", help="random weights (no checkpoint available offline)")
     p.add_argument("--frame_budget", type=int, default=28416, help="max frames per packed batch (111 x 256: whole GEMM waves)")
     p.add_argument("--skip_existing", action="store_true", help="resume: skip files whose .pt already exists")
+    p.add_argument("--window_files", type=int, default=4096,
+                   help="files decoded, batched and encoded at a time (the next window is decoded while this one runs); "
+                        "bounds host memory on a 100k-file corpus")
     p.add_argument("--pooled_path", type=str, default="", help="also save masked-mean pooled embeddings {names, embeddings[N, D]}")
     p.add_argument("--checkpoint", type=str, default="",
                    help="weights file/dir for --ssl_type's architecture; a peft LoRA classifier state dict "
@@ -107,7 +110,11 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
 
     todo = [w for w in wav_files if not (args.skip_existing and os.path.exists(out_path(w)))]
 
-    # ---- host ingest: decode with --num_workers threads ----
+    # ---- rank sharding on FILE SIZE (a PCM WAV's size is its length): every rank decodes only its own files ----
+    sizes = [float(os.path.getsize(os.path.join(args.wav_dir, w))) for w in todo]
+    mine_files = [todo[i] for i in scheduler.shard_by_cost(sizes, world)[rank]]   # ascending size: windows hold similar lengths
+
+    # ---- host ingest: decode with --num_workers threads, one window ahead of the GPU ----
     def load(name):
         path = os.path.join(args.wav_dir, name)
         try:
@@ -121,19 +128,27 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
             print(f"Failed to process {path}: {e}")
             return name, None
 
-    with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:
-        loaded = [(n, y) for n, y in ex.map(load, todo) if y is not None]
-    names = [n for n, _ in loaded]
-    waves = [y for _, y in loaded]
-    lengths = [len(y) for y in waves]
+    win = max(1, args.window_files)
+    windows = [mine_files[i:i + win] for i in range(0, len(mine_files), win)]
+    decoder = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+    writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+
+    def submit_window(k):
+        return [decoder.submit(load, n) for n in windows[k]] if k < len(windows) else []
 
     pooled_rows = {}
-    if waves:
-        batches, mine = scheduler.plan(cfg, lengths, world, rank, frame_budget=args.frame_budget)
-        writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+    n_done = 0
+    pending = submit_window(0)
+    for k in range(len(windows)):
+        loaded = [f.result() for f in pending]
+        pending = submit_window(k + 1)           # decoded while this window is on the GPU
+        names = [n for n, y in loaded if y is not None]
+        waves = [y for _, y in loaded if y is not None]
+        if not waves:
+            continue
         futures = []
-        for bi in mine:
-            idx = batches[bi].indices
+        for bt in scheduler.make_batches(cfg, [len(y) for y in waves], frame_budget=args.frame_budget):
+            idx = bt.indices
             try:
                 if layer >= cfg.num_hidden_layers + 1 or layer < -(cfg.num_hidden_layers + 1):
                     raise IndexError("tuple index out of range")  # what hidden_states[N] raises in the reference
@@ -148,12 +163,14 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
                         pooled_rows[names[i]] = pc[j]
                 for j, i in enumerate(idx):
                     futures.append(writer.submit(torch.save, frames_cpu[j], out_path(names[i])))
+                n_done += len(idx)
             except Exception as e:  # noqa: BLE001
                 for i in idx:
                     print(f"Failed to process {os.path.join(args.wav_dir, names[i])}: {e}")
         for f in futures:
             f.result()
-        writer.shutdown()
+    decoder.shutdown()
+    writer.shutdown()
 
     if args.pooled_path:
         rows = pooled_rows
@@ -171,7 +188,7 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
             keys = sorted(rows)
             emb = torch.stack([rows[k] for k in keys]) if keys else torch.empty(0, cfg.hidden_size)
             torch.save({"names": keys, "embeddings": emb}, args.pooled_path)
-    print(f"Done: {len(names)} utterances on rank {rank}/{world}.")
+    print(f"Done: {n_done} utterances on rank {rank}/{world}.")
     return 0
 
 

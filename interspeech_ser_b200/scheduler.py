@@ -89,6 +89,21 @@ def shard_batches(batches: Sequence[Batch], world_size: int) -> List[List[int]]:
     return assign
 
 
+def shard_by_cost(costs: Sequence[float], world_size: int) -> List[List[int]]:
+    """Greedy LPT over single items (e.g. files, cost = size on disk as a proxy for audio length): heaviest first onto
+    the least-loaded rank. Each rank's list comes back sorted by cost (then index), so that consecutive windows of it
+    hold utterances of similar length. Deterministic; every index appears on exactly one rank."""
+    loads = [0.0] * world_size
+    assign: List[List[int]] = [[] for _ in range(world_size)]
+    for i in sorted(range(len(costs)), key=lambda j: (-costs[j], j)):
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        assign[r].append(i)
+        loads[r] += costs[i]
+    for a in assign:
+        a.sort(key=lambda j: (costs[j], j))
+    return assign
+
+
 def plan(cfg: EncoderConfig, lengths: Sequence[int], world_size: int, rank: int, **kw) -> Tuple[List[Batch], List[int]]:
     """Batches for the whole corpus and the indices of the batches this rank runs."""
     batches = make_batches(cfg, lengths, **kw)

@@ -335,7 +335,10 @@ def test_cli_speech_contract(tmp_path, capsys):
     assert pooled["embeddings"].shape == (3, cfg.hidden_size) and len(pooled["names"]) == 3
     # --n_layer is honoured (intended behaviour); the literal directory-count indexing is opt-in (defect D1)
     out2 = tmp_path / "feat_l0"
-    assert main_speech(["--ssl_type", "tiny/wavlm", "--wav_dir", str(wav_dir), "--save_path", str(out2), "--random_init", "--n_layer", "0"]) == 0
+    # (two files per decode window: the streamed driver loop with its one-window-ahead decode)
+    assert main_speech(["--ssl_type", "tiny/wavlm", "--wav_dir", str(wav_dir), "--save_path", str(out2), "--random_init", "--n_layer", "0",
+                        "--window_files", "2"]) == 0
+    assert sorted(os.listdir(out2)) == sorted(os.path.splitext(k)[0] + ".pt" for k in lens)
     k = "MSP-PODCAST_0001_0001.wav"
     y, _ = audio_io.load_audio(str(wav_dir / k))
     t0 = torch.load(out2 / "MSP-PODCAST_0001_0001.pt")

@@ -121,6 +121,23 @@ def test_mel_filters_and_sinusoids():
     assert pos.shape == (1500, 1280) and np.allclose(pos[0, :640], 0) and np.allclose(pos[0, 640:], 1)
 
 
+def test_shard_by_cost_partitions_files_and_balances():
+    """File-level rank sharding of the CLI (cost = size on disk): a partition, deterministic, LPT-balanced, and each
+    rank's list ascending in cost so that its decode windows hold similar lengths."""
+    rng = np.random.default_rng(3)
+    costs = [float(v) for v in rng.integers(64_000, 640_000, size=1000)]
+    for world in (1, 2, 8):
+        assign = scheduler.shard_by_cost(costs, world)
+        assert sorted(i for a in assign for i in a) == list(range(1000))
+        assert scheduler.shard_by_cost(costs, world) == assign
+        loads = [sum(costs[i] for i in a) for a in assign]
+        assert max(loads) - min(loads) <= max(costs)
+        for a in assign:
+            assert [costs[i] for i in a] == sorted(costs[i] for i in a)
+    assert scheduler.shard_by_cost([], 4) == [[], [], [], []]
+    assert scheduler.shard_by_cost([5.0], 2) == [[0], []]
+
+
 def test_scheduler_batches_cover_every_utterance_once():
     cfg = configs.get_config("microsoft/wavlm-large")
     rng = np.random.default_rng(0)

@@ -55,3 +55,37 @@ def test_two_rank_shard_and_gather(tmp_path):
     assert torch.equal(pooled, ref)                     # same matrix as a single rank would produce, in corpus order
     assert sorted(owners[0] + owners[1]) == list(range(64)) and owners[0] and owners[1]
     assert not set(owners[0]) & set(owners[1])
+
+
+def _cli_shard_worker(rank, world, port, sizes, lens, out_dir):
+    """The CLI's N>1 path: ranks shard FILES by size on disk (no decode of other ranks' files), run their windows
+    through make_batches locally, and rank 0 gathers {name: pooled row}."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = configs.get_config("microsoft/wavlm-large")
+    mine = scheduler.shard_by_cost(sizes, world)[rank]
+    rows = {}
+    for w0 in range(0, len(mine), 5):                     # decode windows of 5 files
+        window = mine[w0:w0 + 5]
+        for bt in scheduler.make_batches(cfg, [lens[i] for i in window], frame_budget=2048):
+            for j in bt.indices:
+                rows[window[j]] = _fake_embed(lens[window[j]])
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(rows, gathered, dst=0)
+    if rank == 0:
+        torch.save(torch.stack(scheduler.merge_rank_results(gathered, len(lens))), os.path.join(out_dir, "pooled_cli.pt"))
+        torch.save([sum(sizes[i] for i in g) for g in gathered], os.path.join(out_dir, "loads.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_cli_file_sharding(tmp_path):
+    rng = np.random.default_rng(9)
+    lens = [int(v) for v in rng.integers(32000, 320000, size=41)]
+    sizes = [44.0 + 2.0 * n for n in lens]                # PCM16 WAV: header + 2 bytes per sample
+    port = _free_port()
+    mp.spawn(_cli_shard_worker, args=(2, port, sizes, lens, str(tmp_path)), nprocs=2, join=True)
+    pooled = torch.load(tmp_path / "pooled_cli.pt")
+    assert torch.equal(pooled, torch.stack([_fake_embed(n) for n in lens]))
+    loads = torch.load(tmp_path / "loads.pt")
+    assert abs(loads[0] - loads[1]) <= max(sizes)
