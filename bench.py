@@ -255,7 +255,7 @@ def run_ours(args):
 
         def step_e2e():
             for hb, ls, ph in zip(hosts, blens, pooled_hosts):
-                out = model.extract_device(hb.to(dev, non_blocking=True), ls, average=True, want_frames=False, want_pooled=True).pooled
+                out = model.extract_pinned(hb, ls, average=True, want_frames=False, want_pooled=True).pooled
                 ph.copy_(out, non_blocking=True)
 
         pooled_host = pooled_hosts[-1]
@@ -266,6 +266,7 @@ def run_ours(args):
         # every rank owns a different shard of the synthetic corpus (seed 7 = the scripts' default --seed)
         host = torch.from_numpy(synth_batch(7 + 1000 * rank, batch, n)).pin_memory()
         lens = [n] * batch
+        host_flat = host.reshape(-1)
         wav_dev = host.to(dev).reshape(-1).contiguous()
         secs_total = batch * secs
         h2d_bytes = host.numel() * 4
@@ -276,8 +277,9 @@ def run_ours(args):
         pooled_host = torch.empty((batch, cfg.hidden_size), dtype=torch.float32).pin_memory()
 
         def step_e2e():
-            w = host.to(dev, non_blocking=True).reshape(-1)
-            out = model.extract_device(w, lens, average=True, want_frames=False, want_pooled=True).pooled
+            # the public call for packed pinned input: upload through the model's two-slot ring on its copy stream (the
+            # transfer of step i+1 runs under the encode of step i), encode, pooled rows back to pinned host memory
+            out = model.extract_pinned(host_flat, lens, average=True, want_frames=False, want_pooled=True).pooled
             pooled_host.copy_(out, non_blocking=True)
 
     def barrier():

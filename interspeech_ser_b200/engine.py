@@ -37,6 +37,51 @@ def layer_mask_of(indices: Iterable[int], num_layers: int) -> Tuple[int, List[in
     return mask, idx
 
 
+class UploadRing:
+    """Copy/compute overlap for a stream of packed batches (one host thread, two streams per GPU).
+
+    `upload(host)` copies a pinned 1-D fp32 tensor into one of `slots` device buffers on a dedicated copy stream and
+    makes the CURRENT stream wait for that copy only. A slot is reused `slots` uploads later, after the compute that
+    read it (marked by `release`). Because kernel launches are asynchronous, the host reaches the next `upload` while
+    the GPU is still encoding the previous batch, so the transfer of batch i+1 runs under the encode of batch i."""
+
+    def __init__(self, device: torch.device, slots: int = 2):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device)
+        self._bufs: List[Optional[torch.Tensor]] = [None] * slots
+        self._free: List[Optional[torch.cuda.Event]] = [None] * slots
+        self._i = 0
+
+    def upload(self, host: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        assert host.dtype == torch.float32 and host.dim() == 1 and not host.is_cuda
+        if not host.is_pinned():
+            host = host.pin_memory()
+        s = self._i % len(self._bufs)
+        self._i += 1
+        n = host.numel()
+        cur = torch.cuda.current_stream(self.device)
+        buf = self._bufs[s]
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)   # allocated on the compute stream ...
+            buf.record_stream(self.copy_stream)                                       # ... and written on the copy stream
+            self._bufs[s] = buf
+            self.copy_stream.wait_stream(cur)    # the allocator may hand back memory the compute stream is still using
+        if self._free[s] is not None:
+            self.copy_stream.wait_event(self._free[s])
+        with torch.cuda.stream(self.copy_stream):
+            buf[:n].copy_(host, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        cur.wait_event(done)
+        return buf[:n], s
+
+    def release(self, slot: int) -> None:
+        """Everything enqueued on the current stream so far may read the slot; later uploads into it wait for that."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[slot] = ev
+
+
 class Engine:
     """One encoder replica on one GPU."""
 

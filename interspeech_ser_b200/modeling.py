@@ -13,6 +13,7 @@ selected / averaged hidden states and masked-mean pooled embeddings out, normali
 from __future__ import annotations
 
 import os
+import threading
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
@@ -22,7 +23,7 @@ import torch
 
 from . import weights as W
 from .configs import ARCH_WHISPER, EncoderConfig, get_config, w2v_num_frames
-from .engine import REDUCE_MEAN, REDUCE_NONE, Engine
+from .engine import REDUCE_MEAN, REDUCE_NONE, Engine, UploadRing
 from .feature_extraction import Wav2Vec2FeatureExtractor, WhisperFeatureExtractor, WhisperProcessor
 
 
@@ -85,6 +86,24 @@ class _Base:
         self.engine = Engine(cfg, tensors, device)
         self.device = self.engine.device
         self.training = False
+        self._ring_tls = threading.local()   # one upload ring per calling thread (the CLI's workers share the model)
+
+    def _upload(self, host: torch.Tensor):
+        ring = getattr(self._ring_tls, "ring", None)
+        if ring is None:
+            ring = self._ring_tls.ring = UploadRing(self.device)
+        wav, slot = ring.upload(host)
+        return ring, wav, slot
+
+    @torch.no_grad()
+    def extract_pinned(self, host: torch.Tensor, lens: Sequence[int], **kw) -> "Extracted":
+        """extract() for utterances already packed back to back in one pinned host tensor: the upload goes through a
+        two-slot ring on a copy stream, so in a loop over batches it overlaps the previous batch's encode."""
+        with torch.cuda.device(self.device):
+            ring, wav, slot = self._upload(host.reshape(-1))
+            res = self.extract_device(wav, lens, **kw)
+            ring.release(slot)
+        return res
 
     # nn.Module-ish no-ops the scripts call
     def eval(self):
@@ -160,8 +179,7 @@ class SpeechEncoderModel(_Base):
         preprocess_speech.py:56-63) per utterance + masked-mean pooled vectors. One H2D copy, one encode call."""
         lens = [int(len(w)) for w in waveforms]
         flat = torch.from_numpy(np.concatenate([np.asarray(w, dtype=np.float32) for w in waveforms]))
-        wav = flat.pin_memory().to(self.device, non_blocking=True)
-        return self.extract_device(wav, lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled)
+        return self.extract_pinned(flat.pin_memory(), lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled)
 
     @torch.no_grad()
     def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
@@ -224,8 +242,8 @@ class WhisperModel(_Base):
         reproducing the script's `feats.shape[1]`, else 1500)."""
         waveforms = [np.asarray(w, dtype=np.float32)[:480000] for w in waveforms]
         lens = [int(len(w)) for w in waveforms]
-        wav = torch.from_numpy(np.concatenate(waveforms)).pin_memory().to(self.device, non_blocking=True)
-        return self.extract_device(wav, lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled,
+        flat = torch.from_numpy(np.concatenate(waveforms)).pin_memory()
+        return self.extract_pinned(flat, lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled,
                                    literal_crop=literal_crop)
 
     @torch.no_grad()

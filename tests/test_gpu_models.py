@@ -125,6 +125,23 @@ def test_baseline_config0_batching_invariance_and_determinism():
     assert a.shape == (8, 1024) and torch.isfinite(a).all()
 
 
+def test_upload_ring_overlapped_batches_match_direct_calls():
+    """extract_pinned (two-slot upload ring on a copy stream) over a run of different batches, sizes growing
+    and shrinking so that slots are re-allocated and reused, without any host synchronisation in between: every result
+    equals the plain device-resident call bit for bit."""
+    cfg, w, model = get_model("tiny/wavlm")
+    batches = []
+    for k, (nb, n) in enumerate([(3, 8000), (5, 16000), (2, 4001), (6, 16000), (1, 32000), (4, 8000), (3, 8000)]):
+        lens = [n - 37 * j for j in range(nb)]
+        host = torch.from_numpy(np.concatenate([synth_wave(500 + 10 * k + j, m) for j, m in enumerate(lens)])).pin_memory()
+        batches.append((host, lens))
+    got = [model.extract_pinned(h, lens, average=True, want_frames=False, want_pooled=True).pooled for h, lens in batches]
+    torch.cuda.synchronize()
+    for (h, lens), g in zip(batches, got):
+        ref = model.extract_device(h.to(model.device), lens, average=True, want_frames=False, want_pooled=True).pooled
+        assert torch.equal(g, ref)
+
+
 def test_encode_call_is_cuda_graph_capturable():
     """SURVEY 8b ownership row: no hidden allocation or synchronisation on the call path, so one encode call through
     the C ABI (span upload, every kernel, pooling) can be captured into a CUDA graph and replayed on new waveform
