@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import argparse
 import os
+import time
 import sys
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
@@ -132,21 +133,28 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     windows = [mine_files[i:i + win] for i in range(0, len(mine_files), win)]
     decoder = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
     writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+    from .engine import DownloadRing
+    downloads = DownloadRing(device)
 
     def submit_window(k):
         return [decoder.submit(load, n) for n in windows[k]] if k < len(windows) else []
 
     pooled_rows = {}
+    pooled_pending = []
+    futures = []
     n_done = 0
+    timing = {"decode_wait": 0.0, "encode_call": 0.0, "download_call": 0.0, "writer_drain": 0.0} if os.environ.get("SERENC_CLI_TIMING") else None
     pending = submit_window(0)
     for k in range(len(windows)):
+        tt = time.time()
         loaded = [f.result() for f in pending]
+        if timing is not None:
+            timing["decode_wait"] += time.time() - tt
         pending = submit_window(k + 1)           # decoded while this window is on the GPU
         names = [n for n, y in loaded if y is not None]
         waves = [y for _, y in loaded if y is not None]
         if not waves:
             continue
-        futures = []
         for bt in scheduler.make_batches(cfg, [len(y) for y in waves], frame_budget=args.frame_budget):
             idx = bt.indices
             try:
@@ -155,22 +163,51 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
                 kw = dict(layer=layer, average=average, want_frames=True, want_pooled=bool(args.pooled_path))
                 if whisper:
                     kw["literal_crop"] = not args.crop_cap_1500
+                tt = time.time()
                 res = model.extract([waves[i] for i in idx], **kw)
-                frames_cpu = [f.cpu().contiguous() for f in res.frames]  # D2H; contiguous clone (no 1500-frame storage behind a view)
-                if res.pooled is not None:
-                    pc = res.pooled.cpu()
-                    for j, i in enumerate(idx):
-                        pooled_rows[names[i]] = pc[j]
-                for j, i in enumerate(idx):
-                    futures.append(writer.submit(torch.save, frames_cpu[j], out_path(names[i])))
+                if timing is not None:
+                    timing["encode_call"] += time.time() - tt
+                    tt = time.time()
+                # one D2H of the packed frames on the copy stream into a pinned ring; a writer thread waits for it, clones
+                # each utterance's rows (contiguous tensors that own their storage: no 1500-frame storage behind a view,
+                # defect D3) and saves them, while this thread goes on to the next batch
+                host, done, slot = downloads.download(res.packed)
+                if timing is not None:
+                    timing["download_call"] += time.time() - tt
+                pooled_dev = res.pooled
+                paths = [out_path(names[i]) for i in idx]
+
+                def write_batch(host=host, done=done, slot=slot, ranges=res.ranges, paths=paths, keep=res.packed):
+                    try:
+                        done.synchronize()
+                        for (a, e), path in zip(ranges, paths):
+                            try:
+                                torch.save(host[a:e].clone(), path)
+                            except Exception as ex:  # noqa: BLE001  (reference: error-and-continue per file)
+                                print(f"Failed to process {path}: {ex}")
+                    finally:
+                        downloads.release(slot)
+                futures.append(writer.submit(write_batch))
+                if pooled_dev is not None:   # pooled rows come back asynchronously too; resolved after the last batch
+                    pc = torch.empty(pooled_dev.shape, dtype=torch.float32).pin_memory()
+                    pc.copy_(pooled_dev, non_blocking=True)
+                    pooled_pending.append((pc, [names[i] for i in idx]))
                 n_done += len(idx)
             except Exception as e:  # noqa: BLE001
                 for i in idx:
                     print(f"Failed to process {os.path.join(args.wav_dir, names[i])}: {e}")
-        for f in futures:
-            f.result()
+    tt = time.time()
+    for f in futures:        # writers drain (the download ring's slots are their back-pressure on the loop above)
+        f.result()
     decoder.shutdown()
     writer.shutdown()
+    torch.cuda.synchronize(device)
+    if timing is not None:
+        timing["writer_drain"] = time.time() - tt
+        print("host time per phase [s] (main thread): " + ", ".join(f"{k} {v:.2f}" for k, v in timing.items()))
+    for pc, ns in pooled_pending:
+        for j, n in enumerate(ns):
+            pooled_rows[n] = pc[j].clone()
 
     if args.pooled_path:
         rows = pooled_rows

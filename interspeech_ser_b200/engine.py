@@ -82,6 +82,46 @@ class UploadRing:
         self._free[slot] = ev
 
 
+class DownloadRing:
+    """Frame-level results back to the host without stalling the GPU: the packed [rows, d] result of a
+    batch is copied on a copy stream into one of `slots` pinned buffers; the caller gets the pinned view and an event
+    and hands both to a writer thread (which waits for the event, clones each utterance's rows and saves them) while
+    the main thread launches the next batch. A slot is only reused after `release(slot)`."""
+
+    def __init__(self, device: torch.device, slots: int = 3):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device)
+        self._bufs: List[Optional[torch.Tensor]] = [None] * slots
+        self._busy = [threading.Event() for _ in range(slots)]
+        for e in self._busy:
+            e.set()          # set = free
+        self._i = 0
+
+    def download(self, packed: torch.Tensor) -> Tuple[torch.Tensor, torch.cuda.Event, int]:
+        assert packed.is_cuda and packed.is_contiguous()
+        s = self._i % len(self._bufs)
+        self._i += 1
+        self._busy[s].wait()                       # back-pressure: the writers are `slots` batches behind
+        self._busy[s].clear()
+        n = packed.numel()
+        buf = self._bufs[s]
+        if buf is None or buf.numel() < n:
+            buf = self._bufs[s] = torch.empty(n, dtype=packed.dtype).pin_memory()
+        host = buf[:n].view(packed.shape)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))    # the encode that produces `packed`
+        packed.record_stream(self.copy_stream)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            host.copy_(packed, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        return host, done, s
+
+    def release(self, slot: int) -> None:
+        self._busy[slot].set()
+
+
 class Engine:
     """One encoder replica on one GPU."""
 

@@ -77,6 +77,8 @@ class Extracted:
     frames: Optional[List[torch.Tensor]]   # per utterance [T_keep, d] fp32 (views into one packed device tensor)
     pooled: Optional[torch.Tensor]         # [B, d] fp32 masked-mean embeddings
     num_frames: List[int]
+    packed: Optional[torch.Tensor] = None  # the [rows, d] device tensor `frames` are views of (one D2H moves them all)
+    ranges: Optional[List[Tuple[int, int]]] = None   # row range of every utterance inside `packed`
 
 
 class _Base:
@@ -192,13 +194,14 @@ class SpeechEncoderModel(_Base):
         layers, reduce = self._select(layer, average)
         frames, pooled, offs, _ = self.engine.encode_w2v(wav, starts, lens, normalize=self.cfg.do_normalize, layers=layers,
                                                          reduce=reduce, want_frames=want_frames, want_pooled=want_pooled)
-        per_utt = None
+        per_utt, f2, ranges = None, None, None
         if frames is not None:
             f2 = frames if reduce == REDUCE_MEAN else frames[0]
-            per_utt = [f2[offs[b]:offs[b + 1]] for b in range(len(lens))]
+            ranges = [(offs[b], offs[b + 1]) for b in range(len(lens))]
+            per_utt = [f2[a:e] for a, e in ranges]
         if pooled is not None and reduce == REDUCE_NONE:
             pooled = pooled[0]
-        return Extracted(per_utt, pooled, [offs[b + 1] - offs[b] for b in range(len(lens))])
+        return Extracted(per_utt, pooled, [offs[b + 1] - offs[b] for b in range(len(lens))], f2, ranges)
 
 
 class WhisperEncoder:
@@ -259,13 +262,14 @@ class WhisperModel(_Base):
         layers, reduce = self._select(layer, average)
         frames, pooled, _ = self.engine.encode_whisper(mel, layers=layers, reduce=reduce, n_keep=keep, want_frames=want_frames,
                                                        want_pooled=want_pooled)
-        per_utt = None
+        per_utt, f2, ranges = None, None, None
         if frames is not None:
             f2 = frames if reduce == REDUCE_MEAN else frames[0]
-            per_utt = [f2[b * 1500: b * 1500 + keep[b]] for b in range(len(lens))]
+            ranges = [(b * 1500, b * 1500 + keep[b]) for b in range(len(lens))]
+            per_utt = [f2[a:e] for a, e in ranges]
         if pooled is not None and reduce == REDUCE_NONE:
             pooled = pooled[0]
-        return Extracted(per_utt, pooled, keep)
+        return Extracted(per_utt, pooled, keep, f2, ranges)
 
 
 # --------------------------------------------------------------------------------------------------
