@@ -98,7 +98,8 @@ struct serenc_handle {
   float* pos_emb = nullptr;             // [1500, d]
   int mel_pad = 128;                    // n_mels rounded up to 64
   std::vector<float> mel_filters_host;  // [201, n_mels]
-  float *hann = nullptr, *costab = nullptr, *sintab = nullptr, *mel_w = nullptr;
+  float *hann = nullptr, *mel_w = nullptr;
+  float2* twid = nullptr;   // log-mel twiddle matrix [99][256] (logmel.cuh)
   int32_t *mel_ptr = nullptr, *mel_bin = nullptr;
 
   std::mutex mu;
@@ -1007,11 +1008,18 @@ extern "C" int serenc_finalize(serenc_handle* h) {
   if (c.arch == SERENC_ARCH_WHISPER) {
     std::vector<float> hann(LM_NFFT), ct(LM_NFFT), stb(LM_NFFT);
     const double PI = 3.14159265358979323846;
-    for (int i = 0; i < LM_NFFT; ++i) {
-      hann[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / LM_NFFT));  // torch.hann_window(400), periodic
-      ct[i] = (float)cos(2.0 * PI * i / LM_NFFT);
-      stb[i] = (float)sin(2.0 * PI * i / LM_NFFT);
-    }
+    for (int i = 0; i < LM_NFFT; ++i) hann[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / LM_NFFT));  // torch.hann_window(400), periodic
+    // twiddles of the folded DFT: row n - 1 (n = 1..99), column t = thread of logmel_power_kernel, bin k = 2 (t % 128) + t / 128;
+    // the angle is reduced exactly (n k mod 400) before the double-precision cos / sin
+    std::vector<float> tw((size_t)99 * 256 * 2, 0.f);
+    for (int n = 1; n < 100; ++n)
+      for (int t = 0; t < 256; ++t) {
+        const int k = 2 * (t & 127) + (t >> 7);
+        if (k >= LM_BINS) continue;
+        const int m = (n * k) % LM_NFFT;
+        tw[((size_t)(n - 1) * 256 + t) * 2 + 0] = (float)cos(2.0 * PI * m / LM_NFFT);
+        tw[((size_t)(n - 1) * 256 + t) * 2 + 1] = (float)sin(2.0 * PI * m / LM_NFFT);
+      }
     std::vector<int32_t> ptr(c.n_mels + 1, 0), bin;
     std::vector<float> w;
     for (int m = 0; m < c.n_mels; ++m) {
@@ -1021,9 +1029,10 @@ extern "C" int serenc_finalize(serenc_handle* h) {
       }
       ptr[m + 1] = (int32_t)bin.size();
     }
-    SERENC_TRY(dev_alloc(h, &h->hann, LM_NFFT)); SERENC_TRY(dev_alloc(h, &h->costab, LM_NFFT)); SERENC_TRY(dev_alloc(h, &h->sintab, LM_NFFT));
+    SERENC_TRY(dev_alloc(h, &h->hann, LM_NFFT));
+    { float* twp = nullptr; SERENC_TRY(dev_alloc(h, &twp, tw.size())); h->twid = reinterpret_cast<float2*>(twp); }
     SERENC_TRY(dev_alloc(h, &h->mel_ptr, ptr.size())); SERENC_TRY(dev_alloc(h, &h->mel_bin, bin.size())); SERENC_TRY(dev_alloc(h, &h->mel_w, w.size()));
-    SERENC_TRY(upload_f32(h->hann, hann.data(), LM_NFFT)); SERENC_TRY(upload_f32(h->costab, ct.data(), LM_NFFT)); SERENC_TRY(upload_f32(h->sintab, stb.data(), LM_NFFT));
+    SERENC_TRY(upload_f32(h->hann, hann.data(), LM_NFFT)); SERENC_TRY(upload_f32(reinterpret_cast<float*>(h->twid), tw.data(), tw.size()));
     SERENC_CUDA_OK(cudaMemcpy(h->mel_ptr, ptr.data(), ptr.size() * 4, cudaMemcpyHostToDevice));
     SERENC_CUDA_OK(cudaMemcpy(h->mel_bin, bin.data(), bin.size() * 4, cudaMemcpyHostToDevice));
     SERENC_TRY(upload_f32(h->mel_w, w.data(), w.size()));
@@ -1565,7 +1574,7 @@ extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64
   uint32_t* umax = reinterpret_cast<uint32_t*>(scratch_dev);
   SERENC_CUDA_OK(cudaMemsetAsync(umax, 0, 4 * (size_t)batch, st));
   LogmelTables tb;
-  tb.hann = h->hann; tb.costab = h->costab; tb.sintab = h->sintab;
+  tb.hann = h->hann; tb.twid = h->twid;
   tb.mel_ptr = h->mel_ptr; tb.mel_bin = h->mel_bin; tb.mel_w = h->mel_w; tb.n_mels = h->cfg.n_mels;
   const dim3 grid(ceil_div(LM_FRAMES, LM_FR), batch);
   ProfScope ps(h, SERENC_PROF_LOGMEL, 3, 0.0, (double)batch * (4.0 * LM_NSAMP + 4.0 * h->cfg.n_mels * LM_FRAMES), st);
