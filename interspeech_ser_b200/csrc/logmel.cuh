@@ -7,12 +7,12 @@
 // (n <-> 400-n symmetry of cos/sin, then n <-> 200-n symmetry split by bin parity), which leaves 99 cos +
 // 99 sin MACs per bin instead of 400 + 400.
 //
-// One CTA computes LM_FR = 16 consecutive frames of one utterance; one THREAD owns one frequency bin and keeps the
-// real / imaginary sums of all 16 frames in registers (as fp32x2 pairs of frames, FFMA2). Per folded sample n it
+// One CTA computes LM_FR = 16 consecutive frames of one utterance; one THREAD owns LM_BPT = 2 frequency bins and keeps
+// their real / imaginary sums of all 16 frames in registers (as fp32x2 pairs of frames, FFMA2). Per folded sample n it
 // needs its own twiddle (cos, sin)(2 pi n k / 400) - one coalesced 8-byte load from a precomputed [99][256] matrix
 // (L2-resident, 203 KB) - and the folded samples of the 16 frames, stored frame-contiguous in shared memory so that
-// they arrive as broadcast LDS.128. Warps 0-3 own the even bins, warps 4-7 the odd ones (the fold differs by bin
-// parity, so a warp reads one address). That is 10 loads per 32 FMAs; the previous form (one (frame, bin) per thread,
+// they arrive as broadcast LDS.128. The lower half of the CTA owns the even bins, the upper half the odd ones (the fold
+// differs by bin parity, so a warp reads one address). That is 10 loads per 32 FMAs; the previous form (one (frame, bin) per thread,
 // twiddles gathered from a 400-entry shared-memory table with bank conflicts) issued 4 loads per 2 FMAs and ran at
 // 1.5 TFMA/s. Power spectrum -> shared memory -> mel projection through a CSR copy of the (sparse, triangular)
 // filterbank, output written [B, n_mels, 3000] with frames contiguous. Pass 2 applies the per-utterance
@@ -30,7 +30,8 @@ constexpr int LM_FRAMES = 3000;
 constexpr int LM_FR = 16;                                   // frames per CTA
 constexpr int LM_SPAN = (LM_FR - 1) * LM_HOP + LM_NFFT;     // samples touched by one CTA
 constexpr int LM_FOLD = 400;                                // per-frame folded layout, see below
-constexpr int LM_THREADS = 256;
+constexpr int LM_BPT = 2;                                    // bins per thread (registers: LM_BPT x LM_FR sums, re + im); measured 1 / 2 / 4: 0.74 / 0.64 / 0.89 ms
+constexpr int LM_THREADS = 256 / LM_BPT;
 
 // order-preserving float <-> uint map so atomicMax works on signed floats
 __device__ __forceinline__ uint32_t float_to_ordered(float f) {
@@ -105,48 +106,71 @@ __global__ void __launch_bounds__(LM_THREADS) logmel_power_kernel(const float* _
   }
   __syncthreads();   // s_xp (samples) is dead from here on
 
-  // DFT: this thread's bin for all LM_FR frames
-  const int odd = tid >> 7;                 // warps 0-3: even bins, warps 4-7: odd bins
-  const int k = 2 * (tid & 127) + odd;
-  uint64_t re2[LM_FR / 2], im2[LM_FR / 2];  // frame pairs (f, f + 1)
+  // DFT: this thread's LM_BPT bins for all LM_FR frames. Thread t: parity = upper half of the CTA, bins
+  // k_j = 2 * (t % H + j * H) + parity with H = LM_THREADS / 2 lanes per parity (twiddle column = (k_j / 2) + 128 * parity).
+  // Every folded sample loaded from shared memory feeds LM_BPT FMAs: broadcast LDS.128 costs 4 shared-memory
+  // wavefronts whatever the number of lanes that need it, so bins per thread is what buys the FMA rate.
+  constexpr int H = LM_THREADS / 2;
+  const int odd = tid / H;
+  const int idx0 = tid - odd * H;
+  uint64_t re2[LM_BPT][LM_FR / 2], im2[LM_BPT][LM_FR / 2];  // frame pairs (f, f + 1)
 #pragma unroll
-  for (int j = 0; j < LM_FR / 2; ++j) re2[j] = im2[j] = 0ull;
-  if (k < LM_BINS) {   // warp-uniform except in the last warp of each parity
-    const float2* tw = tb.twid + tid;
+  for (int j = 0; j < LM_BPT; ++j)
+#pragma unroll
+    for (int q = 0; q < LM_FR / 2; ++q) re2[j][q] = im2[j][q] = 0ull;
+  {
+    const float2* tw = tb.twid + idx0 + 128 * odd;     // + j * H per bin; columns of bins > 200 hold zeros
     const uint4* ce = reinterpret_cast<const uint4*>(&s_fold[odd ? 1 : 0][0][0]);   // [n][LM_FR / 4]
     const uint4* so = reinterpret_cast<const uint4*>(&s_fold[odd ? 3 : 2][0][0]);
-    float2 t_nxt = __ldg(tw);
-#pragma unroll 3
+    float2 t_nxt[LM_BPT];
+#pragma unroll
+    for (int j = 0; j < LM_BPT; ++j) t_nxt[j] = __ldg(tw + j * H);
+#pragma unroll 1
     for (int n = 1; n < 100; ++n) {
-      const float2 t = t_nxt;
-      if (n < 99) t_nxt = __ldg(tw + n * 256);
-      const uint64_t c2 = pack_f32x2(t.x, t.x), s2 = pack_f32x2(t.y, t.y);
+      uint64_t c2[LM_BPT], s2[LM_BPT];
+#pragma unroll
+      for (int j = 0; j < LM_BPT; ++j) {
+        c2[j] = pack_f32x2(t_nxt[j].x, t_nxt[j].x);
+        s2[j] = pack_f32x2(t_nxt[j].y, t_nxt[j].y);
+        if (n < 99) t_nxt[j] = __ldg(tw + n * 256 + j * H);
+      }
 #pragma unroll
       for (int q = 0; q < LM_FR / 4; ++q) {
         const uint4 cv = ce[n * (LM_FR / 4) + q], sv = so[n * (LM_FR / 4) + q];
-        re2[2 * q] = ffma2(pack_f32x2(__uint_as_float(cv.x), __uint_as_float(cv.y)), c2, re2[2 * q]);
-        re2[2 * q + 1] = ffma2(pack_f32x2(__uint_as_float(cv.z), __uint_as_float(cv.w)), c2, re2[2 * q + 1]);
-        im2[2 * q] = ffma2(pack_f32x2(__uint_as_float(sv.x), __uint_as_float(sv.y)), s2, im2[2 * q]);
-        im2[2 * q + 1] = ffma2(pack_f32x2(__uint_as_float(sv.z), __uint_as_float(sv.w)), s2, im2[2 * q + 1]);
+        const uint64_t ca = pack_f32x2(__uint_as_float(cv.x), __uint_as_float(cv.y)), cb = pack_f32x2(__uint_as_float(cv.z), __uint_as_float(cv.w));
+        const uint64_t sa = pack_f32x2(__uint_as_float(sv.x), __uint_as_float(sv.y)), sb = pack_f32x2(__uint_as_float(sv.z), __uint_as_float(sv.w));
+#pragma unroll
+        for (int j = 0; j < LM_BPT; ++j) {
+          re2[j][2 * q] = ffma2(ca, c2[j], re2[j][2 * q]);
+          re2[j][2 * q + 1] = ffma2(cb, c2[j], re2[j][2 * q + 1]);
+          im2[j][2 * q] = ffma2(sa, s2[j], im2[j][2 * q]);
+          im2[j][2 * q + 1] = ffma2(sb, s2[j], im2[j][2 * q + 1]);
+        }
       }
     }
     // specials: n = 0, n = 200 (sign (-1)^k), n = 100 (cos(pi k/2), sin(pi k/2))
     const float sgn = odd ? -1.f : 1.f;
-    const int q4 = k & 3;
-    const float c100 = (q4 == 0) ? 1.f : (q4 == 2 ? -1.f : 0.f);
-    const float s100 = (q4 == 1) ? 1.f : (q4 == 3 ? -1.f : 0.f);
 #pragma unroll
-    for (int j = 0; j < LM_FR / 2; ++j) {
-      float r0, r1, i0, i1;
-      unpack_f32x2(re2[j], r0, r1);
-      unpack_f32x2(im2[j], i0, i1);
-      const int fa = 2 * j, fb = 2 * j + 1;
-      const float rea = r0 + s_fold[0][0][fa] + sgn * s_fold[1][0][fa] + c100 * s_fold[2][0][fa];
-      const float reb = r1 + s_fold[0][0][fb] + sgn * s_fold[1][0][fb] + c100 * s_fold[2][0][fb];
-      const float ima = i0 + s100 * s_fold[3][0][fa];
-      const float imb = i1 + s100 * s_fold[3][0][fb];
-      s_xp[fa * PW_LD + k] = rea * rea + ima * ima;
-      s_xp[fb * PW_LD + k] = reb * reb + imb * imb;
+    for (int j = 0; j < LM_BPT; ++j) {
+      const int k = 2 * (idx0 + j * H) + odd;
+      if (k < LM_BINS) {
+        const int q4 = k & 3;
+        const float c100 = (q4 == 0) ? 1.f : (q4 == 2 ? -1.f : 0.f);
+        const float s100 = (q4 == 1) ? 1.f : (q4 == 3 ? -1.f : 0.f);
+#pragma unroll
+        for (int q = 0; q < LM_FR / 2; ++q) {
+          float r0, r1, i0, i1;
+          unpack_f32x2(re2[j][q], r0, r1);
+          unpack_f32x2(im2[j][q], i0, i1);
+          const int fa = 2 * q, fb = 2 * q + 1;
+          const float rea = r0 + s_fold[0][0][fa] + sgn * s_fold[1][0][fa] + c100 * s_fold[2][0][fa];
+          const float reb = r1 + s_fold[0][0][fb] + sgn * s_fold[1][0][fb] + c100 * s_fold[2][0][fb];
+          const float ima = i0 + s100 * s_fold[3][0][fa];
+          const float imb = i1 + s100 * s_fold[3][0][fb];
+          s_xp[fa * PW_LD + k] = rea * rea + ima * ima;
+          s_xp[fb * PW_LD + k] = reb * reb + imb * imb;
+        }
+      }
     }
   }
   __syncthreads();
