@@ -197,20 +197,35 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__
       }
       continue;
     }
-    uint64_t s2 = fadd2(fadd2(fadd2(a[0], a[1]), fadd2(a[2], a[3])), fadd2(fadd2(a[4], a[5]), fadd2(a[6], a[7])));
-    float s_lo, s_hi;
-    unpack_f32x2(s2, s_lo, s_hi);
-    const float mu = warp_sum(s_lo + s_hi) * (1.f / CONV0_C);
-    const uint64_t nmu2 = pack_f32x2(-mu, -mu);
-    uint64_t q2 = 0ull;   // (+0.0f, +0.0f)
+    // LayerNorm statistics in ONE butterfly: sum and sum of squares about a per-frame pivot (this lane-0 channel's
+    // value, broadcast) travel through the five shuffle rounds together, so a frame pays one reduction latency
+    // instead of two dependent ones (8 warps per SM cannot hide them). Shifting by the pivot keeps the one-pass
+    // variance free of the |mean| >> std cancellation.
+    float a00, a01;
+    unpack_f32x2(a[0], a00, a01);
+    const float pivot = __shfl_sync(0xffffffffu, a00, 0);
+    const uint64_t npv2 = pack_f32x2(-pivot, -pivot);
+    uint64_t s2 = 0ull, q2 = 0ull;   // (+0.0f, +0.0f)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      a[i] = fadd2(a[i], nmu2);          // centred values, reused below
+      a[i] = fadd2(a[i], npv2);          // values about the pivot, reused below
+      s2 = fadd2(s2, a[i]);
       q2 = ffma2(a[i], a[i], q2);
     }
-    float q_lo, q_hi;
+    float s_lo, s_hi, q_lo, q_hi;
+    unpack_f32x2(s2, s_lo, s_hi);
     unpack_f32x2(q2, q_lo, q_hi);
-    const float rs = rsqrtf(warp_sum(q_lo + q_hi) * (1.f / CONV0_C) + 1e-5f);
+    float sv = s_lo + s_hi, qv = q_lo + q_hi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      qv += __shfl_xor_sync(0xffffffffu, qv, o);
+    }
+    const float mu = sv * (1.f / CONV0_C);                       // mean about the pivot
+    const float rs = rsqrtf(fmaxf(qv * (1.f / CONV0_C) - mu * mu, 0.f) + 1e-5f);
+    const uint64_t nmu2 = pack_f32x2(-mu, -mu);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fadd2(a[i], nmu2);        // centred values
     const uint64_t rs2 = pack_f32x2(rs, rs);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
