@@ -108,6 +108,34 @@ def test_wavlm_large_vs_hf_golden(golden_dir):
     print(f"wavlm-large worst cosine {worst[0]:.6f}, worst max-rel {worst[1]:.3e}")
 
 
+@pytest.mark.parametrize("name", ["facebook/hubert-xlarge-ls960-ft", "facebook/wav2vec2-xls-r-2b"])
+def test_xlarge_models_vs_hf_golden(golden_dir, name):
+    """Full-size HuBERT-xlarge (48 layers, d = 1280, head_dim 80) and XLS-R-2b (48 layers, d = 1920, head_dim 120):
+    BASELINE configs[2] / [3] architectures, every hidden state of a 0.25 s + 6 s packed batch against the HF fp32
+    forward on the same seeded weights (the wide-head tcgen05 attention, the 10 / 15-vector LayerNorm widths and the
+    padded positional-conv groups at their real sizes)."""
+    g = load_golden(golden_dir, name)
+    cfg, w, model = get_model(name)
+    lens = [int(n) for n in g["lengths"]]
+    waves = [synth_wave(int(g["wave_seed_base"]) + j, n) for j, n in enumerate(lens)]
+    L = cfg.num_hidden_layers
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).tolist()
+    wav = torch.from_numpy(np.concatenate(waves)).cuda()
+    _, pooled, offs, _ = model.engine.encode_w2v(wav, starts, lens, normalize=True, layers=range(L + 1), want_frames=False, want_pooled=True)
+    torch.cuda.synchronize()
+    worst = (1.0, 0.0)
+    for b in range(len(lens)):
+        for i in range(L + 1):
+            cos, rel = check_embedding(pooled[i, b], torch.from_numpy(g[f"pooled_{b}"][i]), f"{name} utt{b} hs{i}")
+            worst = (min(worst[0], cos), max(worst[1], rel))
+    res = model.extract(waves, average=True, want_frames=False, want_pooled=True)
+    for b in range(len(lens)):
+        check_embedding(res.pooled[b], torch.from_numpy(g[f"meanlast4_pooled_{b}"]), f"{name} utt{b} mean-last-4")
+    print(f"{name} worst cosine {worst[0]:.6f}, worst max-rel {worst[1]:.3e}")
+    _MODELS.pop(name, None)  # free the host copy of the weights (3.8 / 8.7 GB)
+    del model
+
+
 def test_baseline_config0_batching_invariance_and_determinism():
     """BASELINE configs[0]: WavLM-large, batch 8 x 4 s. The embedding of an utterance must not depend on its batch
     (the reference runs batch 1): packed batch == one-by-one == permuted batch, bit for bit, and twice the same."""
