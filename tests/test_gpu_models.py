@@ -136,6 +136,34 @@ def test_xlarge_models_vs_hf_golden(golden_dir, name):
     del model
 
 
+def test_baseline_config2_length_bucketed_batching_invariance():
+    """BASELINE configs[2]: HuBERT-xlarge over variable-length 2-12 s utterances. Size-independent property at full
+    model size: an utterance's embedding in a ragged packed batch (scheduler order) equals, bit for bit, the one it
+    gets alone or in a permuted batch - packed rows, ragged attention tiles and per-utterance pooling never mix
+    utterances, and no kernel's reduction order depends on the batch."""
+    from interspeech_ser_b200 import scheduler
+    name = "facebook/hubert-xlarge-ls960-ft"
+    cfg, w, model = get_model(name)
+    rng = np.random.default_rng(11)
+    lens = [int(v) for v in rng.integers(2 * 16000, 12 * 16000, size=12)]
+    waves = [synth_wave(700 + j, n) for j, n in enumerate(lens)]
+    batches = scheduler.make_batches(cfg, lens, frame_budget=4096)
+    assert len(batches) >= 1 and sorted(i for b in batches for i in b.indices) == list(range(12))
+    got = {}
+    for bt in batches:
+        res = model.extract([waves[i] for i in bt.indices], average=True, want_frames=False, want_pooled=True).pooled.cpu()
+        for j, i in enumerate(bt.indices):
+            got[i] = res[j]
+    for i in (0, 5, 11):
+        alone = model.extract([waves[i]], average=True, want_frames=False, want_pooled=True).pooled.cpu()[0]
+        assert torch.equal(alone, got[i])
+    rev = model.extract([waves[i] for i in reversed(range(12))], average=True, want_frames=False, want_pooled=True).pooled.cpu()
+    for j, i in enumerate(reversed(range(12))):
+        assert torch.equal(rev[j], got[i])
+    assert all(torch.isfinite(v).all() for v in got.values())
+    _MODELS.pop(name, None)
+
+
 def test_baseline_config0_batching_invariance_and_determinism():
     """BASELINE configs[0]: WavLM-large, batch 8 x 4 s. The embedding of an utterance must not depend on its batch
     (the reference runs batch 1): packed batch == one-by-one == permuted batch, bit for bit, and twice the same."""
