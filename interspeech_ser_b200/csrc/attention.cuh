@@ -10,7 +10,11 @@
 //   per-row gate  g = a * (b * const_h - 1) + 2,  (a, b) = sigmoid(sum4(gru_rel_pos_linear(x_i,head)))
 //   is computed in the kernel prologue from the layer input.
 //
-// Tensor-core path: mma.sync m16n8k16 bf16 (fp32 accumulate), ldmatrix from XOR-swizzled shared memory,
+// THIS FILE: the shared parameter block and the first-generation kernel, kept as the A/B arm (SERENC_ATTN_MMA_SYNC=1)
+// and as the fallback for combinations the tcgen05 kernels do not cover (gated bias with head_dim 80 / 120: no such
+// checkpoint exists). The production kernels are attention_tc.cuh (head_dim 64, WavLM bias) and attention_tc_wide.cuh
+// (head_dim 80 / 120).
+// Tensor-core path here: mma.sync m16n8k16 bf16 (fp32 accumulate), ldmatrix from XOR-swizzled shared memory,
 // cp.async double-buffered K/V tiles. One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows.
 // head_dim 64 / 80 / 120 (80 and 120 are zero-padded to 128 columns in shared memory only).
 #pragma once
