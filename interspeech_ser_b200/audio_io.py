@@ -11,18 +11,28 @@ from typing import Tuple
 import numpy as np
 
 
-def read_wav(path: str) -> Tuple[np.ndarray, int]:
+def read_bytes(path: str) -> bytes:
+    """The I/O half of read_wav (releases the GIL: this is what the CLI's worker threads run)."""
     with open(path, "rb") as fh:
-        data = fh.read()
+        return fh.read()
+
+
+def read_wav(path: str) -> Tuple[np.ndarray, int]:
+    return decode_wav(read_bytes(path), path)
+
+
+def decode_wav(data: bytes, path: str = "<bytes>") -> Tuple[np.ndarray, int]:
+    """RIFF/WAVE bytes -> (mono float32, sample rate). One pass over the samples, no copy of the payload."""
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError(f"{path}: not a RIFF/WAVE file")
+    view = memoryview(data)
     pos = 12
     fmt = None
     payload = None
     while pos + 8 <= len(data):
         cid = data[pos:pos + 4]
-        size = struct.unpack("<I", data[pos + 4:pos + 8])[0]
-        body = data[pos + 8:pos + 8 + size]
+        size = struct.unpack_from("<I", data, pos + 4)[0]
+        body = view[pos + 8:pos + 8 + size]
         if cid == b"fmt ":
             tag, ch, sr, _, _, bits = struct.unpack("<HHIIHH", body[:16])
             if tag == 0xFFFE and len(body) >= 26:  # WAVE_FORMAT_EXTENSIBLE: sub-format GUID starts with the real tag
@@ -36,7 +46,8 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
     tag, ch, sr, bits = fmt
     if tag == 1:
         if bits == 16:
-            x = np.frombuffer(payload, dtype="<i2").astype(np.float32) / 32768.0
+            x = np.frombuffer(payload[: len(payload) // 2 * 2], dtype="<i2").astype(np.float32)
+            x *= np.float32(1.0 / 32768.0)   # exact (power of two), in place
         elif bits == 8:
             x = (np.frombuffer(payload, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
         elif bits == 32:
@@ -59,7 +70,11 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
 
 def load_audio(path: str, sr: int = 16000) -> Tuple[np.ndarray, int]:
     """librosa.load(path, sr=16000) stand-in: mono float32 at `sr`."""
-    x, file_sr = read_wav(path)
+    return load_audio_bytes(read_bytes(path), path, sr)
+
+
+def load_audio_bytes(data: bytes, path: str = "<bytes>", sr: int = 16000) -> Tuple[np.ndarray, int]:
+    x, file_sr = decode_wav(data, path)
     if file_sr != sr:
         from math import gcd
 

@@ -56,7 +56,7 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     args = build_parser(whisper).parse_args(argv)
     import torch
 
-    from .audio_io import load_audio
+    from .audio_io import load_audio_bytes, read_bytes
     from .configs import ARCH_WHISPER
     from .modeling import AutoModel
     from . import scheduler
@@ -115,11 +115,14 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     sizes = [float(os.path.getsize(os.path.join(args.wav_dir, w))) for w in todo]
     mine_files = [todo[i] for i in scheduler.shard_by_cost(sizes, world)[rank]]   # ascending size: windows hold similar lengths
 
-    # ---- host ingest: decode with --num_workers threads, one window ahead of the GPU ----
-    def load(name):
+    # ---- host ingest, one window ahead of the GPU ----
+    # Measured (tools/bench_decode.py, 8-vCPU container): PCM decode is memory- and GIL-bound: inline 15 k audio-s/s,
+    # 4 threads 19 k, 8 threads 7 k (they fight over the interpreter), reader threads + one decoder thread 11 k. So:
+    # at most 4 decode threads however large --num_workers is, each task a chunk of 16 files.
+    def decode_one(name):
         path = os.path.join(args.wav_dir, name)
         try:
-            y, _ = load_audio(path, sr=16000)
+            y, _ = load_audio_bytes(read_bytes(path), path, sr=16000)
             if not whisper and len(y) < 400:
                 raise ValueError(f"{len(y)} samples is shorter than the encoder's 400-sample receptive field")
             if len(y) == 0:
@@ -129,15 +132,23 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
             print(f"Failed to process {path}: {e}")
             return name, None
 
+    def decode_chunk(names_chunk):
+        return [decode_one(n) for n in names_chunk]
+
     win = max(1, args.window_files)
     windows = [mine_files[i:i + win] for i in range(0, len(mine_files), win)]
-    decoder = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+    readers = ThreadPoolExecutor(max_workers=max(1, min(4, args.num_workers)))
+    decoder = ThreadPoolExecutor(max_workers=1)          # owns a window: the main thread only waits on one future
     writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
     from .engine import DownloadRing
     downloads = DownloadRing(device)
 
+    def decode_window(names_w):
+        chunks = [names_w[i:i + 16] for i in range(0, len(names_w), 16)]
+        return [r for c in readers.map(decode_chunk, chunks) for r in c]
+
     def submit_window(k):
-        return [decoder.submit(load, n) for n in windows[k]] if k < len(windows) else []
+        return decoder.submit(decode_window, windows[k]) if k < len(windows) else None
 
     pooled_rows = {}
     pooled_pending = []
@@ -147,7 +158,7 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     pending = submit_window(0)
     for k in range(len(windows)):
         tt = time.time()
-        loaded = [f.result() for f in pending]
+        loaded = pending.result()
         if timing is not None:
             timing["decode_wait"] += time.time() - tt
         pending = submit_window(k + 1)           # decoded while this window is on the GPU
@@ -200,6 +211,7 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     for f in futures:        # writers drain (the download ring's slots are their back-pressure on the loop above)
         f.result()
     decoder.shutdown()
+    readers.shutdown()
     writer.shutdown()
     torch.cuda.synchronize(device)
     if timing is not None:

@@ -121,6 +121,30 @@ def test_mel_filters_and_sinusoids():
     assert pos.shape == (1500, 1280) and np.allclose(pos[0, :640], 0) and np.allclose(pos[0, 640:], 1)
 
 
+def test_wav_bytes_decode_matches_file_decode(tmp_path):
+    """The CLI reads files in I/O threads (read_bytes) and decodes in one thread (load_audio_bytes): same samples as
+    load_audio on the path, for 16-bit PCM, a float32 WAVE and an odd trailing byte; 16-bit scaling is exact."""
+    x = (np.random.default_rng(2).standard_normal(16001) * 0.3).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    audio_io.write_wav(p, x)
+    y_file, sr = audio_io.load_audio(p)
+    y_bytes, sr2 = audio_io.load_audio_bytes(audio_io.read_bytes(p), p)
+    assert sr == sr2 == 16000 and np.array_equal(y_file, y_bytes) and y_bytes.dtype == np.float32
+    pcm = np.clip(np.round(x.astype(np.float64) * 32768.0), -32768, 32767).astype(np.int16)
+    assert np.array_equal(y_bytes, pcm.astype(np.float32) / 32768.0)
+    data = audio_io.read_bytes(p)
+    y_odd, _ = audio_io.decode_wav(data[:-1], "truncated")          # data chunk one byte short: whole samples only
+    assert len(y_odd) == len(x) - 1 and np.array_equal(y_odd, y_bytes[:-1])
+    import struct
+    f32 = x.astype("<f4").tobytes()
+    wav = (b"RIFF" + struct.pack("<I", 36 + len(f32)) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 16000, 64000, 4, 32) +
+           b"data" + struct.pack("<I", len(f32)) + f32)
+    yf, _ = audio_io.decode_wav(wav, "float")
+    assert np.array_equal(yf, x)
+    with pytest.raises(ValueError):
+        audio_io.decode_wav(b"garbage", "broken")
+
+
 def test_shard_by_cost_partitions_files_and_balances():
     """File-level rank sharding of the CLI (cost = size on disk): a partition, deterministic, LPT-balanced, and each
     rank's list ascending in cost so that its decode windows hold similar lengths."""
