@@ -280,7 +280,7 @@ def main():
         if want("microsoft/wavlm-large"):
             golden_w2v("microsoft/wavlm-large", [4001, 64000, 192000], atol=5e-4)
         if want("openai/whisper-large-v3"):
-            golden_whisper("openai/whisper-large-v3", [64000], atol=5e-4)
+            golden_whisper("openai/whisper-large-v3", [64000, 16000, 496000], atol=5e-4)
         if want("facebook/hubert-xlarge-ls960-ft"):
             golden_w2v("facebook/hubert-xlarge-ls960-ft", [4001, 96000], atol=5e-4)
         if want("facebook/wav2vec2-xls-r-2b"):
