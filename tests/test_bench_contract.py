@@ -1,0 +1,35 @@
+"""bench.py's reference arm (CPU): the JSON line the driver parses, and the torchrun convention that only rank 0 works."""
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    env.pop("WORLD_SIZE", None)
+    env.update(extra_env or {})
+    return subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=env, cwd=REPO, timeout=600)
+
+
+def test_reference_arm_prints_one_contract_line():
+    res = _run()
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "audio-seconds/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("audio-seconds/sec encoded") and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "utterances" in cb["sample"]
+    assert d["config"]["model"] == "microsoft/wavlm-large" and "workload" in d["config"] and d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    res = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
