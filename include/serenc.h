@@ -19,6 +19,11 @@
  *    when each call uses its own stream and workspace (the reference drives one model from 4 threads,
  *    preprocess_speech.py:120-122).
  *  - there is no CPU fallback: without a CUDA device of compute capability 10.x serenc_create fails.
+ *  - kernel faults are sticky: once an entry point has seen a CUDA error that invalidates the context (illegal
+ *    address, launch failure, ... - the errors CUDA itself reports on every later call) the handle is POISONED:
+ *    every further call on it returns SERENC_ERR_CUDA with the original message, serenc_is_poisoned() returns 1,
+ *    and only serenc_destroy() is useful. Kernels run asynchronously, so a fault surfaces at the next call on
+ *    the handle or at serenc_sync(), which callers should use where the reference would have read a result.
  */
 #ifndef SERENC_H_
 #define SERENC_H_
@@ -42,14 +47,24 @@ typedef enum {
 } serenc_status;
 
 typedef enum {
-  SERENC_ARCH_W2V = 0,    /* Wav2Vec2Model / HubertModel / WavLMModel (HF modeling_wav2vec2.py, modular_hubert.py, modeling_wavlm.py) */
-  SERENC_ARCH_WHISPER = 1 /* WhisperEncoder (HF modeling_whisper.py:541-647) */
+  SERENC_ARCH_W2V = 0,     /* Wav2Vec2Model / HubertModel / WavLMModel (HF modeling_wav2vec2.py, modular_hubert.py, modeling_wavlm.py) */
+  SERENC_ARCH_WHISPER = 1, /* WhisperEncoder (HF modeling_whisper.py:541-647) */
+  SERENC_ARCH_TEXT = 2     /* RobertaModel: token/position/type embeddings + post-LN encoder (HF modeling_roberta.py;
+                              preprocessing/preprocess_roberta.py:48-74 of the reference) */
 } serenc_arch;
 
 typedef enum {
-  SERENC_REDUCE_NONE = 0, /* emit every selected hidden state                                             */
-  SERENC_REDUCE_MEAN = 1  /* emit the mean over the selected hidden states (preprocess_speech.py:56-63)   */
+  SERENC_REDUCE_NONE = 0,    /* emit every selected hidden state                                             */
+  SERENC_REDUCE_MEAN = 1,    /* emit the mean over the selected hidden states (preprocess_speech.py:56-63)   */
+  SERENC_REDUCE_WEIGHTED = 2 /* emit sum_i w_i * hidden_states[sel_i] with caller-supplied weights (the softmax-
+                                weighted layer sum of lora_wavlm/model.py:164-181; the caller applies the softmax) */
 } serenc_reduce;
+
+typedef enum {
+  SERENC_WAV_F32 = 0, /* float32 samples (what librosa.load returns, preprocess_speech.py:47)                */
+  SERENC_WAV_I16 = 1  /* int16 PCM as stored in the WAV file; the kernels apply librosa's x / 32768 on load,  */
+                      /* bit-identical to the float path at half the host decode work and H2D bytes          */
+} serenc_wav_dtype;
 
 /* Architecture constants (the fields of the HF config.json this path depends on). */
 typedef struct {
@@ -71,7 +86,11 @@ typedef struct {
   int32_t conv_group_norm;      /* W2V: 1 = feat_extract_norm "group" (base checkpoints): GroupNorm on conv0 only */
   int32_t post_layer_norm;      /* W2V: 1 = do_stable_layer_norm false (base checkpoints): post-LN encoder layers  */
   int32_t no_feat_proj_ln;      /* W2V: 1 = feature projection without LayerNorm (HuBERT-base)                     */
-  int32_t reserved[5];
+  int32_t vocab_size;           /* TEXT: rows of the word embedding (roberta: 50265)                               */
+  int32_t max_positions;        /* TEXT: rows of the position embedding (roberta: 514)                             */
+  int32_t type_vocab_size;      /* TEXT: rows of the token-type embedding (roberta: 1)                             */
+  int32_t pad_token_id;         /* TEXT: padding_idx; position ids start at pad_token_id + 1 (roberta: 1)          */
+  int32_t reserved[1];
 } serenc_config;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------ */
@@ -93,6 +112,11 @@ int serenc_finalize(serenc_handle* h);
 
 const char* serenc_last_error(void);
 const char* serenc_version(void);
+
+/* Waits for everything enqueued on `stream` and reports (and records, see "sticky" above) a kernel fault. */
+int serenc_sync(serenc_handle* h, void* stream);
+/* 1 once a sticky CUDA error was observed through this handle, else 0. */
+int serenc_is_poisoned(const serenc_handle* h);
 
 /* ---- wav2vec2 / HuBERT / WavLM -------------------------------------------------------------------- */
 
@@ -132,9 +156,39 @@ int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const int64_t* sam
                       float* pooled_out_dev, int64_t* frame_offsets_out, void* workspace_dev, size_t workspace_bytes,
                       void* stream);
 
+/* The same call with every optional input / output (a zero-initialised struct with the fields of serenc_encode_w2v
+ * set behaves exactly like it):
+ *   wav_dtype                 serenc_wav_dtype of wav_dev (sample_start counts samples either way)
+ *   layer_weights             host, [number of selected layers], ascending layer index; SERENC_REDUCE_WEIGHTED only
+ *   extract_features_out_dev  fp32 [sum_T, conv_dim]: the feature projection's LayerNorm output, HF's
+ *                             `extract_features` (modeling_wavlm.py:93-105); NULL = not wanted. Needs a
+ *                             feature-projection LayerNorm (HubertModel returns no extract_features). */
+typedef struct {
+  const void* wav_dev;
+  int32_t wav_dtype;
+  int32_t batch;
+  const int64_t* sample_start;
+  const int32_t* sample_len;
+  int32_t normalize;
+  int32_t reduce;
+  uint64_t layer_mask;
+  const float* layer_weights;
+  float* frames_out_dev;
+  float* pooled_out_dev;
+  float* extract_features_out_dev;
+  int64_t* frame_offsets_out;
+  void* workspace_dev;
+  size_t workspace_bytes;
+  void* stream;
+} serenc_w2v_call;
+int serenc_encode_w2v_ex(serenc_handle* h, const serenc_w2v_call* call);
+
 /* packed [sum_T, hidden] -> HF-shaped padded [batch, t_max, hidden] (pad frames = 0). */
 int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
                          int32_t t_max, float* out_dev, void* stream);
+/* The same for rows of any width (`cols` % 4 == 0), e.g. extract_features [sum_T, 512]. */
+int serenc_unpack_rows(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
+                       int32_t t_max, int32_t cols, float* out_dev, void* stream);
 
 /* ---- Whisper -------------------------------------------------------------------------------------- */
 
@@ -143,6 +197,10 @@ int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, const int64_
  * mel_out_dev is [batch, n_mels, 3000] fp32. scratch_dev: at least 64 + 40*batch bytes. */
 int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
                   int batch, float* mel_out_dev, void* scratch_dev, void* stream);
+
+/* serenc_logmel for int16 PCM or float32 samples (wav_dtype = serenc_wav_dtype). */
+int serenc_logmel_ex(serenc_handle* h, const void* wav_dev, int wav_dtype, const int64_t* sample_start,
+                     const int32_t* sample_len, int batch, float* mel_out_dev, void* scratch_dev, void* stream);
 
 int serenc_whisper_workspace_bytes(const serenc_handle* h, int batch, size_t* out_bytes);
 
@@ -154,6 +212,27 @@ int serenc_whisper_workspace_bytes(const serenc_handle* h, int batch, size_t* ou
 int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
                           const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev, void* workspace_dev,
                           size_t workspace_bytes, void* stream);
+
+/* serenc_encode_whisper + SERENC_REDUCE_WEIGHTED: layer_weights is host, [number of selected layers]. */
+int serenc_encode_whisper_ex(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
+                             const float* layer_weights, const int32_t* n_keep, float* frames_out_dev,
+                             float* pooled_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- text encoder (RoBERTa) ------------------------------------------------------------------------ */
+
+int serenc_text_workspace_bytes(const serenc_handle* h, int batch, int seq_len, size_t* out_bytes);
+
+/* Replaces RobertaModel(**encoding, output_hidden_states=True) + layer selection (preprocess_roberta.py:48-70):
+ * input_ids_dev is [batch, seq_len] int32 (the tokenizer pads to max_length = 80, :49-55); valid_len (host,
+ * [batch]) = number of leading non-pad tokens of each row, i.e. attention_mask.sum(-1) of a right-padded batch.
+ * Position ids are pad_token_id + 1 + t for t < valid_len and pad_token_id after (HF
+ * create_position_ids_from_input_ids), token types are 0, keys >= valid_len are masked out of every attention.
+ * ALL seq_len rows of every sequence are produced, pad positions included, as the reference saves them:
+ * frames_out_dev is [n_sel, batch * seq_len, hidden] (or [batch * seq_len, hidden] when reducing); hidden_states[0]
+ * is the embedding output after its LayerNorm. pooled_out_dev = mean over the valid_len leading rows. */
+int serenc_encode_text(serenc_handle* h, const int32_t* input_ids_dev, const int32_t* valid_len, int batch, int seq_len,
+                       uint64_t layer_mask, int reduce, const float* layer_weights, float* frames_out_dev,
+                       float* pooled_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---- launch accounting / per-kernel-class device timing (used by bench.py for the roofline numbers) ---- */
 

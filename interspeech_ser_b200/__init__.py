@@ -16,4 +16,7 @@ def __getattr__(name):
     if name in ("AutoModel", "AutoFeatureExtractor", "AutoProcessor", "SpeechEncoderModel", "WhisperModel"):
         from . import modeling
         return getattr(modeling, name)
+    if name in ("RobertaModel", "RobertaTokenizer"):   # text branch (preprocessing/preprocess_roberta.py)
+        from . import text
+        return getattr(text, name)
     raise AttributeError(name)

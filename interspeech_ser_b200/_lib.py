@@ -19,8 +19,11 @@ EXPORTED_SYMBOLS = [
     "serenc_encode_w2v", "serenc_unpack_frames", "serenc_logmel", "serenc_whisper_workspace_bytes",
     "serenc_encode_whisper", "serenc_op_gemm", "serenc_op_gemm_grouped", "serenc_op_layernorm",
     "serenc_op_attention", "serenc_wavlm_bucket", "serenc_launch_count", "serenc_set_profiling", "serenc_get_profile",
-    "serenc_debug_gemm_trace",
+    "serenc_debug_gemm_trace", "serenc_sync", "serenc_is_poisoned", "serenc_encode_w2v_ex", "serenc_unpack_rows",
+    "serenc_logmel_ex", "serenc_encode_whisper_ex", "serenc_text_workspace_bytes", "serenc_encode_text",
 ]
+
+WAV_F32, WAV_I16 = 0, 1
 
 
 class SerencConfig(C.Structure):
@@ -30,7 +33,20 @@ class SerencConfig(C.Structure):
         ("num_buckets", C.c_int32), ("max_distance", C.c_int32), ("pos_conv_kernel", C.c_int32),
         ("pos_conv_groups", C.c_int32), ("n_mels", C.c_int32), ("max_source_positions", C.c_int32),
         ("layer_norm_eps", C.c_float), ("conv_group_norm", C.c_int32), ("post_layer_norm", C.c_int32),
-        ("no_feat_proj_ln", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("no_feat_proj_ln", C.c_int32), ("vocab_size", C.c_int32), ("max_positions", C.c_int32),
+        ("type_vocab_size", C.c_int32), ("pad_token_id", C.c_int32), ("reserved", C.c_int32 * 1),
+    ]
+
+
+class SerencW2VCall(C.Structure):
+    """serenc_w2v_call (include/serenc.h)."""
+    _fields_ = [
+        ("wav_dev", C.c_void_p), ("wav_dtype", C.c_int32), ("batch", C.c_int32),
+        ("sample_start", C.POINTER(C.c_int64)), ("sample_len", C.POINTER(C.c_int32)),
+        ("normalize", C.c_int32), ("reduce", C.c_int32), ("layer_mask", C.c_uint64),
+        ("layer_weights", C.POINTER(C.c_float)), ("frames_out_dev", C.c_void_p), ("pooled_out_dev", C.c_void_p),
+        ("extract_features_out_dev", C.c_void_p), ("frame_offsets_out", C.POINTER(C.c_int64)),
+        ("workspace_dev", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
     ]
 
 
@@ -52,12 +68,15 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m interspeech_ser_b200.build` "
-                                   "(there is no CPU or PyTorch fallback for this path)")
+        if build_if_missing:
+            # always go through build_library(): it compares the digest of csrc/ with the stamp of the built library
+            # (cheap) and rebuilds when they differ, so an edited kernel is never measured through a stale .so; it
+            # builds into a temporary file under a lock, so concurrent torchrun ranks never load a half-written file
             from .build import build_library
             build_library()
+        elif not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m interspeech_ser_b200.build` "
+                               "(there is no CPU or PyTorch fallback for this path)")
         lib = C.CDLL(LIB_PATH)
         vp, i32, i64, u64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_size_t
         pi32, pi64, pf = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_float)
@@ -85,6 +104,14 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
             "serenc_debug_gemm_trace": (C.c_int, [vp, vp]),
             "serenc_set_profiling": (C.c_int, [vp, C.c_int]),
             "serenc_get_profile": (C.c_int, [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), pi64]),
+            "serenc_sync": (C.c_int, [vp, vp]),
+            "serenc_is_poisoned": (C.c_int, [vp]),
+            "serenc_encode_w2v_ex": (C.c_int, [vp, C.POINTER(SerencW2VCall)]),
+            "serenc_unpack_rows": (C.c_int, [vp, vp, pi64, C.c_int, i32, i32, vp, vp]),
+            "serenc_logmel_ex": (C.c_int, [vp, vp, C.c_int, pi64, pi32, C.c_int, vp, vp, vp]),
+            "serenc_encode_whisper_ex": (C.c_int, [vp, vp, C.c_int, u64, C.c_int, pf, pi32, vp, vp, vp, sz, vp]),
+            "serenc_text_workspace_bytes": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(sz)]),
+            "serenc_encode_text": (C.c_int, [vp, vp, pi32, C.c_int, C.c_int, u64, C.c_int, pf, vp, vp, vp, sz, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
@@ -108,3 +135,7 @@ def i64_array(values):
 def i32_array(values):
     arr = (C.c_int32 * len(values))(*[int(v) for v in values])
     return arr
+
+
+def f32_array(values):
+    return (C.c_float * len(values))(*[float(v) for v in values])

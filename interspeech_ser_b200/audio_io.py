@@ -21,8 +21,11 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
     return decode_wav(read_bytes(path), path)
 
 
-def decode_wav(data: bytes, path: str = "<bytes>") -> Tuple[np.ndarray, int]:
-    """RIFF/WAVE bytes -> (mono float32, sample rate). One pass over the samples, no copy of the payload."""
+def decode_wav(data: bytes, path: str = "<bytes>", keep_int16: bool = False) -> Tuple[np.ndarray, int]:
+    """RIFF/WAVE bytes -> (mono float32, sample rate). One pass over the samples, no copy of the payload.
+    keep_int16: mono 16-bit PCM is returned as the int16 samples themselves (a zero-copy view of `data`); the GPU
+    kernels apply the 1 / 32768 scaling on load (include/serenc.h SERENC_WAV_I16), so host decode work and the
+    upload are halved with bit-identical results."""
     if len(data) < 12 or data[:4] != b"RIFF" or data[8:12] != b"WAVE":
         raise ValueError(f"{path}: not a RIFF/WAVE file")
     view = memoryview(data)
@@ -46,6 +49,8 @@ def decode_wav(data: bytes, path: str = "<bytes>") -> Tuple[np.ndarray, int]:
     tag, ch, sr, bits = fmt
     if tag == 1:
         if bits == 16:
+            if keep_int16 and ch == 1:
+                return np.frombuffer(payload[: len(payload) // 2 * 2], dtype="<i2"), int(sr)
             x = np.frombuffer(payload[: len(payload) // 2 * 2], dtype="<i2").astype(np.float32)
             x *= np.float32(1.0 / 32768.0)   # exact (power of two), in place
         elif bits == 8:
@@ -73,9 +78,11 @@ def load_audio(path: str, sr: int = 16000) -> Tuple[np.ndarray, int]:
     return load_audio_bytes(read_bytes(path), path, sr)
 
 
-def load_audio_bytes(data: bytes, path: str = "<bytes>", sr: int = 16000) -> Tuple[np.ndarray, int]:
-    x, file_sr = decode_wav(data, path)
+def load_audio_bytes(data: bytes, path: str = "<bytes>", sr: int = 16000, keep_int16: bool = False) -> Tuple[np.ndarray, int]:
+    x, file_sr = decode_wav(data, path, keep_int16)
     if file_sr != sr:
+        if x.dtype == np.int16:
+            x = x.astype(np.float32) * np.float32(1.0 / 32768.0)
         from math import gcd
 
         from scipy.signal import resample_poly

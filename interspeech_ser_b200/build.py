@@ -35,16 +35,37 @@ def _source_digest() -> str:
     for f in files:
         with open(f, "rb") as fh:
             hsh.update(fh.read())
+    hsh.update(b"AB_ARMS=" + os.environ.get("SERENC_AB_ARMS", "0").encode())   # compile flags are part of the identity
     return hsh.hexdigest()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into interspeech_ser_b200/libserenc.so for sm_100a. Returns the library path."""
     digest = _source_digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH):
+
+    def up_to_date() -> bool:
+        if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
+            return False
         with open(STAMP_PATH) as fh:
-            if fh.read().strip() == digest:
-                return LIB_PATH
+            return fh.read().strip() == digest
+
+    if not force and up_to_date():
+        return LIB_PATH
+    # one builder at a time (N torchrun ranks import the package at once); the others wait and then find the stamp
+    import fcntl
+    lock = open(os.path.join(PKG_DIR, ".libserenc.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and up_to_date():
+            return LIB_PATH
+        return _compile(digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _compile(digest: str, verbose: bool) -> str:
+    tmp_path = LIB_PATH + f".tmp{os.getpid()}"
     cmd = [
         _nvcc(),
         "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,8 +73,10 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         "--shared", "-Xcompiler", "-fPIC",
         "-cudart", "shared",
         "-I", os.path.join(REPO, "include"),
-        "-o", LIB_PATH,
+        "-o", tmp_path,
     ]
+    if os.environ.get("SERENC_AB_ARMS") == "1":   # development build: getenv kernel switches + the mma.sync attention arm
+        cmd += ["-DSERENC_AB_ARMS"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
@@ -63,6 +86,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libserenc.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
+    os.replace(tmp_path, LIB_PATH)   # atomic: a process that is loading the library sees the old or the new file, never half of one
     with open(STAMP_PATH, "w") as fh:
         fh.write(digest)
     return LIB_PATH

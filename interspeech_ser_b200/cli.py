@@ -40,6 +40,8 @@ def build_parser(whisper: bool) -> argparse.ArgumentParser:
                    help="files decoded, batched and encoded at a time (the next window is decoded while this one runs); "
                         "bounds host memory on a 100k-file corpus")
     p.add_argument("--pooled_path", type=str, default="", help="also save masked-mean pooled embeddings {names, embeddings[N, D]}")
+    p.add_argument("--float_upload", action="store_true",
+                   help="decode 16-bit PCM to float32 on the host (default: upload the int16 samples and scale on the GPU; same result)")
     p.add_argument("--checkpoint", type=str, default="",
                    help="weights file/dir for --ssl_type's architecture; a peft LoRA classifier state dict "
                         "(preprocess_speech_pretrained.py:173) is merged into dense weights at load")
@@ -57,6 +59,9 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     import torch
 
     from .audio_io import load_audio_bytes, read_bytes
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from .configs import ARCH_WHISPER
     from .modeling import AutoModel
     from . import scheduler
@@ -66,17 +71,34 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     if not torch.cuda.is_available():
         print("Error: no CUDA device visible; this extractor has no CPU path.")
         return 2
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     device = torch.device(f"cuda:{local_rank}")
     print(f"Using device = {device}")
 
+    # Under torchrun every rank must shard the SAME work list: rank 0 alone looks at the live save_path (the count
+    # behind --compat_layer_from_dir_count and the --skip_existing filter) and broadcasts what it saw, BEFORE any rank
+    # has written a file. (Ranks load the model at different speeds; a rank listing the directory after another one
+    # started writing would shard a different list: files encoded twice, others never.)
     os.makedirs(args.save_path, exist_ok=True)
-    n_existing = len(os.listdir(args.save_path))
+    wav_files = sorted(os.listdir(args.wav_dir))
+
+    def out_path(name):
+        return os.path.join(args.save_path, os.path.splitext(os.path.basename(name))[0] + ".pt")
+
+    if rank == 0:
+        n_existing = len(os.listdir(args.save_path))
+        todo = [w for w in wav_files if not (args.skip_existing and os.path.exists(out_path(w)))]
+        shared = [n_existing, todo]
+    else:
+        shared = [None, None]
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("gloo")
+        dist.broadcast_object_list(shared, src=0)   # doubles as the barrier that keeps every writer behind rank 0's listing
+    n_existing, todo = shared
     print(f"Save path = {args.save_path} created. It has {n_existing} files in it.")
 
-    wav_files = sorted(os.listdir(args.wav_dir))
     print(f"{len(wav_files)} file are going to be processed...")
     print(f"Checking files in {args.wav_dir}")
     missing = [os.path.join(args.wav_dir, w) for w in wav_files if not os.path.isfile(os.path.join(args.wav_dir, w))]
@@ -106,11 +128,6 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     if not whisper and getattr(args, "compat_layer_from_dir_count", False):
         layer = n_existing  # preprocess_speech.py:41,67
 
-    def out_path(name):
-        return os.path.join(args.save_path, os.path.splitext(os.path.basename(name))[0] + ".pt")
-
-    todo = [w for w in wav_files if not (args.skip_existing and os.path.exists(out_path(w)))]
-
     # ---- rank sharding on FILE SIZE (a PCM WAV's size is its length): every rank decodes only its own files ----
     sizes = [float(os.path.getsize(os.path.join(args.wav_dir, w))) for w in todo]
     mine_files = [todo[i] for i in scheduler.shard_by_cost(sizes, world)[rank]]   # ascending size: windows hold similar lengths
@@ -122,7 +139,7 @@ def run(argv: Optional[List[str]], whisper: bool) -> int:
     def decode_one(name):
         path = os.path.join(args.wav_dir, name)
         try:
-            y, _ = load_audio_bytes(read_bytes(path), path, sr=16000)
+            y, _ = load_audio_bytes(read_bytes(path), path, sr=16000, keep_int16=not args.float_upload)
             if not whisper and len(y) < 400:
                 raise ValueError(f"{len(y)} samples is shorter than the encoder's 400-sample receptive field")
             if len(y) == 0:
@@ -247,3 +264,100 @@ def main_speech(argv: Optional[List[str]] = None) -> int:
 
 def main_whisper(argv: Optional[List[str]] = None) -> int:
     return run(argv, whisper=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# text branch: preprocessing/preprocess_roberta.py
+# --------------------------------------------------------------------------------------------------
+def build_roberta_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser()
+    # the reference's flags (preprocess_roberta.py:13-20)
+    p.add_argument("--seed", type=int, default=7)
+    p.add_argument("--roberta_type", type=str, default="roberta")
+    p.add_argument("--df_path", type=str, default="./")
+    p.add_argument("--save_path", type=str, default="./")
+    p.add_argument("--num_workers", type=int, default=4)
+    p.add_argument("--max_len", type=int, default=80)
+    p.add_argument("--use_average", type=str, default="n")
+    # additions
+    p.add_argument("--random_init", action="store_true", help="random weights (no checkpoint available offline)")
+    p.add_argument("--tokenizer_path", type=str, default="", help="directory with vocab.json + merges.txt (default: --roberta_type)")
+    p.add_argument("--batch_texts", type=int, default=256, help="texts per encode call")
+    p.add_argument("--skip_existing", action="store_true")
+    return p
+
+
+def main_roberta(argv: Optional[List[str]] = None) -> int:
+    """preprocess_roberta.py: CSV (columns `transcription`, `FileName`) -> <basename>.pt holding [max_len, D] fp32 — every
+    position of the max_length-padded sequence, pad positions included, as the reference saves them (:49-74)."""
+    args = build_roberta_parser().parse_args(argv)
+    import pandas as pd
+    import torch
+
+    from .configs import ARCH_TEXT
+    from .modeling import AutoModel
+    from .text import RobertaTokenizer
+
+    average = args.use_average == "y"
+    print(f"Using average = {average}")
+    if not torch.cuda.is_available():
+        print("Error: no CUDA device visible; this extractor has no CPU path.")
+        return 2
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device(f"cuda:{local_rank}")
+    print(f"Using device = {device}")
+    os.makedirs(args.save_path, exist_ok=True)
+    print(f"Save path = {args.save_path} created. It has {len(os.listdir(args.save_path))} files in it.")
+    print(f"Reading dataframe {args.df_path}")
+    try:
+        df = pd.read_csv(args.df_path)
+        texts = [str(t) for t in df.transcription.values]
+        names = [str(n) for n in df.FileName.values]
+    except Exception as e:  # noqa: BLE001  (preprocess_roberta.py:91-95)
+        print(f"Error reading dataframe from {args.df_path}: {e}")
+        print("Something went wrong, make sure everything is correct before running again!")
+        return 1
+    print(f"Extracting features using {args.roberta_type}")
+    try:
+        tokenizer = RobertaTokenizer.from_pretrained(args.tokenizer_path or args.roberta_type)
+        model = AutoModel.from_pretrained(args.roberta_type, device=local_rank, random_init=args.random_init or None, seed=0)
+        if model.cfg.arch != ARCH_TEXT:
+            raise OSError(f"{args.roberta_type} is not a text encoder")
+    except OSError:
+        print(f"Error: No pretrained model found with the name {args.roberta_type}")
+        print("Something went wrong, make sure everything is correct before running again!")
+        return 1
+
+    def out_path(name):
+        return os.path.join(args.save_path, os.path.splitext(os.path.basename(name))[0] + ".pt")
+
+    todo = [i for i in range(len(texts)) if i % world == rank and not (args.skip_existing and os.path.exists(out_path(names[i])))]
+    writer = ThreadPoolExecutor(max_workers=max(1, args.num_workers))
+    futures = []
+    n_done = 0
+    for k in range(0, len(todo), max(1, args.batch_texts)):
+        idx = todo[k:k + max(1, args.batch_texts)]
+        try:
+            enc = tokenizer([texts[i] for i in idx], padding="max_length", truncation=True, max_length=args.max_len, return_tensors="pt")
+            res = model.extract_tokens(enc["input_ids"], enc["attention_mask"], layer=-1, average=average, want_frames=True)
+            host = res.packed.cpu()      # one D2H for the batch
+            T = args.max_len
+
+            def write(host=host, idx=idx, T=T):
+                for j, i in enumerate(idx):
+                    try:
+                        torch.save(host[j * T:(j + 1) * T].clone(), out_path(names[i]))
+                    except Exception as ex:  # noqa: BLE001
+                        print(f"Failed to process {names[i]}: {ex}")
+            futures.append(writer.submit(write))
+            n_done += len(idx)
+        except Exception as e:  # noqa: BLE001  (reference: error-and-continue, :75-76)
+            for i in idx:
+                print(f"Failed to process {names[i]}: {e}")
+    for f in futures:
+        f.result()
+    writer.shutdown()
+    print(f"Done: {n_done} texts on rank {rank}/{world}.")
+    return 0

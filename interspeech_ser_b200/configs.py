@@ -11,12 +11,13 @@ from typing import Dict, Tuple
 
 ARCH_W2V = 0      # Wav2Vec2Model / HubertModel / WavLMModel
 ARCH_WHISPER = 1  # WhisperModel.encoder
+ARCH_TEXT = 2     # RobertaModel (preprocessing/preprocess_roberta.py of the reference)
 
 
 @dataclass(frozen=True)
 class EncoderConfig:
     name: str
-    family: str                   # "wavlm" | "wav2vec2" | "hubert" | "whisper"
+    family: str                   # "wavlm" | "wav2vec2" | "hubert" | "whisper" | "roberta"
     hidden_size: int
     num_hidden_layers: int
     num_attention_heads: int
@@ -42,9 +43,16 @@ class EncoderConfig:
     do_normalize: bool = True
     return_attention_mask: bool = True
     sampling_rate: int = 16000
+    # text encoder (RobertaConfig)
+    vocab_size: int = 0
+    max_position_embeddings: int = 0
+    type_vocab_size: int = 0
+    pad_token_id: int = 1
 
     @property
     def arch(self) -> int:
+        if self.family == "roberta":
+            return ARCH_TEXT
         return ARCH_WHISPER if self.family == "whisper" else ARCH_W2V
 
     @property
@@ -81,9 +89,11 @@ HUBERT_LARGE = _reg(
     "hubert-large-ll60k", "hubert-large")
 # base-size checkpoints: GroupNorm feature encoder, post-LN transformer (benchmark/utils/etc.py:10-15 and
 # configs/old/*wavlmbase* of the reference use them)
+# preprocessor_config.json of wavlm-base / wavlm-base-plus: do_normalize false (only wavlm-large normalises), like the
+# other GroupNorm checkpoints trained on un-normalised audio (recalled from the hub files, not re-verifiable offline)
 WAVLM_BASE_PLUS = _reg(
     EncoderConfig("microsoft/wavlm-base-plus", "wavlm", 768, 12, 12, 3072, conv_bias=False, feat_extract_norm="group",
-                  do_stable_layer_norm=False),
+                  do_stable_layer_norm=False, do_normalize=False, return_attention_mask=True),
     "microsoft/wavlm-base", "wavlm-base-plus", "wavlm-base")
 WAV2VEC2_BASE = _reg(
     EncoderConfig("facebook/wav2vec2-base", "wav2vec2", 768, 12, 12, 3072, conv_bias=False, feat_extract_norm="group",
@@ -102,6 +112,14 @@ WHISPER_LARGE_V2 = _reg(
 WHISPER_MEDIUM = _reg(
     EncoderConfig("openai/whisper-medium", "whisper", 1024, 24, 16, 4096, num_mel_bins=80),
     "whisper-medium")
+
+# Text encoders of the reference's text branch (preprocess_roberta.py:19 `--roberta_type`; post-LN BERT-style stacks)
+_TEXT = dict(layer_norm_eps=1e-5, do_stable_layer_norm=False, vocab_size=50265, max_position_embeddings=514,
+             type_vocab_size=1, pad_token_id=1)
+ROBERTA_LARGE = _reg(EncoderConfig("roberta-large", "roberta", 1024, 24, 16, 4096, **_TEXT), "FacebookAI/roberta-large", "roberta")
+ROBERTA_BASE = _reg(EncoderConfig("roberta-base", "roberta", 768, 12, 12, 3072, **_TEXT), "FacebookAI/roberta-base")
+TINY_ROBERTA = _reg(EncoderConfig("tiny/roberta", "roberta", 128, 2, 2, 256, layer_norm_eps=1e-5, do_stable_layer_norm=False,
+                                  vocab_size=300, max_position_embeddings=130, type_vocab_size=1, pad_token_id=1))
 
 # Tiny configurations for fast known-answer tests (same code paths, seconds on CPU for the oracle).
 TINY_WAVLM = _reg(

@@ -18,6 +18,7 @@
 // cp.async double-buffered K/V tiles. One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows.
 // head_dim 64 / 80 / 120 (80 and 120 are zero-padded to 128 columns in shared memory only).
 #pragma once
+#include "attention_params.cuh"
 #include "common.cuh"
 
 namespace serenc {
@@ -25,30 +26,6 @@ namespace serenc {
 constexpr int ATT_BM = 64;
 constexpr int ATT_BN = 64;
 constexpr int ATT_THREADS = 128;
-constexpr int WAVLM_MAXD = 1024;  // bias table covers delta in [-(MAXD-1), MAXD-1]; clamped beyond (buckets saturate at 778)
-
-struct AttnParams {
-  const bf16* qkv;   // [rows, ld_qkv]: q | k | v, each d wide, head h at columns h*HD
-  int64_t ld_qkv;
-  int d;             // model width (= H * HD)
-  const int32_t* frame_off;  // [B+1]
-  bf16* out;         // [rows, d]
-  float scale;       // head_dim^-0.5
-  // WavLM only
-  const bf16* hln;        // [rows, d] layer input (post-LN) the gate is computed from
-  const float* gru_w;     // [8, HD]
-  const float* gru_b;     // [8]
-  const float* gru_const; // [H]
-  const float* btab;      // [H, 2*WAVLM_MAXD-1]
-  // tcgen05 kernel only
-  float* gate = nullptr;       // [rows, heads] WavLM gate (LayerNorm epilogue or wavlm_gate_kernel writes it, attention_tc_kernel reads it)
-  bool gate_ready = false;     // the LayerNorm that produced hln already filled `gate`
-  int heads = 0, batch = 0;
-  int ntile = 0;               // 128-query tiles per utterance = ceil(tmax / 128)
-  int nwin = 0;                // stride of one bias-window buffer (entries)
-  long long* trace = nullptr;  // debug (serenc_debug_gemm_trace): per-CTA clock stamps
-};
-
 template <int HD>
 struct AttnCfg {
   static constexpr int DP = (HD == 64) ? 64 : 128;          // padded row width in smem (elements)

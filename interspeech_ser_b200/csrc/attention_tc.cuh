@@ -21,7 +21,7 @@
 // row) overlap one CTA's softmax with the others' MMAs and loads.
 // V is consumed as an MN-major (head-dim contiguous) B operand directly from its row-major [key, d] tile.
 #pragma once
-#include "attention.cuh"
+#include "attention_params.cuh"
 #include "common.cuh"
 #include <type_traits>
 
@@ -146,7 +146,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int i0 = blockIdx.x * FA_BM;
   if (i0 >= T) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkv = (T + FA_BN - 1) / FA_BN;
+  const int Tk = p.key_len ? min(T, max(1, p.key_len[b])) : T;   // keys of the utterance that take part (right-padded text batches)
+  const int nkv = (Tk + FA_BN - 1) / FA_BN;
   long long* tr = nullptr;
   if (p.trace && (tid == 0 || tid == 128)) {
     const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -212,7 +213,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       const uint32_t tmem_u = warp_uniform(tmem_base);
       const int r0u = (int)warp_uniform((uint32_t)r0);
-      const int nkv = (int)warp_uniform((uint32_t)((T + FA_BN - 1) / FA_BN));   // shadows the CTA-wide value: uniform for the compiler
+      const int nkv = (int)warp_uniform((uint32_t)((Tk + FA_BN - 1) / FA_BN));   // shadows the CTA-wide value: uniform for the compiler
       const int colq = h * FA_HD, colk = p.d + h * FA_HD, colv = 2 * p.d + h * FA_HD;
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN);                 // Q K^T: both K-major
       constexpr uint32_t idesc_o = umma_idesc_bf16(FA_BM, FA_HD) | (1u << 16);    // P V: B (= V) MN-major
@@ -305,7 +306,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < nkv; ++j) {
       const uint32_t ph = (uint32_t)(j & 1);
       const int j0 = j * FA_BN;
-      const int ncols = min(FA_BN, T - j0);
+      const int ncols = min(FA_BN, Tk - j0);
       mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_s, ph);
       if (j < 4) fa_stamp(tr, 4 + 4 * j);
       tc_fence_after();

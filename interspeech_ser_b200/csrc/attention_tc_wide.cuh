@@ -86,8 +86,9 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int i0 = blockIdx.x * FA_BM;
   if (i0 >= T) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkv = (T + FA_BN - 1) / FA_BN;
-  long long* tr = nullptr;   // debug clock stamps, same slots as attention_tc_kernel (tests/trace_attn.py)
+  const int Tk = p.key_len ? min(T, max(1, p.key_len[b])) : T;   // keys that take part (see AttnParams::key_len)
+  const int nkv = (Tk + FA_BN - 1) / FA_BN;
+  long long* tr = nullptr;   // debug clock stamps, same slots as attention_tc_kernel (tools/trace_attn.py)
   if (p.trace && (tid == 0 || tid == 128)) {
     const int lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const int idx = lin < 32 ? lin : (lin >= 2048 && lin < 2080 ? lin - 2048 + 32 : -1);
@@ -232,7 +233,7 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int j0 = j * FA_BN;
-      const int ncols = min(FA_BN, T - j0);
+      const int ncols = min(FA_BN, Tk - j0);
       const uint32_t t_s = t_lane + ((j & 1) ? C::TMEM_S1 : C::TMEM_S0);
       mbar_wait_relaxed<FA_WAIT_HINT_NS>(bar_s + (j & 1), (uint32_t)((j >> 1) & 1));
       if (j < 4) fa_stamp(tr, 4 + 4 * j);

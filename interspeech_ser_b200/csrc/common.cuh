@@ -29,6 +29,14 @@ struct UttSpan {
   int32_t pad_;
 };
 
+// Sample `idx` of a waveform buffer that holds float32 samples or int16 PCM (include/serenc.h serenc_wav_dtype). int16
+// is scaled by 1 / 32768 exactly as librosa / soundfile do when they hand the reference float32 samples
+// (preprocess_speech.py:47), so both forms give bit-identical results.
+__device__ __forceinline__ float load_sample(const void* wav, int is_i16, int64_t idx) {
+  return is_i16 ? (float)reinterpret_cast<const int16_t*>(wav)[idx] * (1.0f / 32768.0f)
+                : reinterpret_cast<const float*>(wav)[idx];
+}
+
 // ---------------------------------------------------------------------------------------------
 // small math
 // ---------------------------------------------------------------------------------------------
@@ -435,12 +443,14 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // ---------------------------------------------------------------------------------------------
 namespace serenc {
 void set_error(const char* fmt, ...);
+void note_cuda_error(int cuda_error);   // remembered per thread: the entry-point guard decides whether it poisons the handle
 }
 
 #define SERENC_CUDA_OK(expr)                                                                        \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \
     if (_e != cudaSuccess) {                                                                        \
+      serenc::note_cuda_error((int)_e);                                                             \
       serenc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return SERENC_ERR_CUDA;                                                                       \
     }                                                                                               \

@@ -10,18 +10,18 @@ namespace serenc {
 // (Wav2Vec2FeatureExtractor.zero_mean_unit_var_norm, HF feature_extraction_wav2vec2.py:77-97;
 //  population variance, two-pass like numpy's). One block per utterance.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) wav_stats_kernel(const float* __restrict__ wav,
+__global__ void __launch_bounds__(1024) wav_stats_kernel(const void* __restrict__ wav, int wav_i16,
                                                           const UttSpan* __restrict__ utts,
                                                           float2* __restrict__ stats /*[B] (mean, rstd)*/) {
   const int b = blockIdx.x;
-  const float* x = wav + utts[b].sample_start;
+  const int64_t x0 = utts[b].sample_start;
   const int n = utts[b].sample_len;
   __shared__ double red[32];
   __shared__ float s_mean;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)load_sample(wav, wav_i16, x0 + i);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) red[warp] = acc;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(1024) wav_stats_kernel(const float* __restrict
   const float mean = s_mean;
   acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = x[i] - mean;
+    const float d = load_sample(wav, wav_i16, x0 + i) - mean;
     acc += (double)(d * d);
   }
 #pragma unroll
@@ -90,7 +90,7 @@ typedef UttSpan Conv0Utt;
 // MODE 2: GroupNorm apply pass: conv recomputed (10 MACs per output beat a 1 KB round trip), y = gelu(a*scale + shift)
 //         with the per-(utterance, channel) scale/shift produced by conv0_gn_finalize_kernel.
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__ wav,
+__global__ void __launch_bounds__(256, 1) conv0_kernel(const void* __restrict__ wav, int wav_i16,
                                                        const Conv0Utt* __restrict__ utts,
                                                        const float2* __restrict__ stats,  // nullptr: already normalised
                                                        const float* __restrict__ w,       // [512][10]
@@ -130,10 +130,9 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const float* __restrict__
     mean = st.x;
     rstd = st.y;
   }
-  const float* x = wav + u.sample_start;
   for (int i = threadIdx.x; i < CONV0_TILE * CONV0_S + CONV0_K; i += blockDim.x) {
     const int64_t s = (int64_t)t0 * CONV0_S + i;
-    xs[i] = s < u.sample_len ? (x[s] - mean) * rstd : 0.f;
+    xs[i] = s < u.sample_len ? (load_sample(wav, wav_i16, u.sample_start + s) - mean) * rstd : 0.f;
   }
   __syncthreads();
 
@@ -506,7 +505,10 @@ __global__ void accum_scaled_kernel(float* __restrict__ acc, const float* __rest
 __global__ void __launch_bounds__(256) masked_mean_pool_kernel(const float* __restrict__ x, int d,
                                                                 const int32_t* __restrict__ frame_off /*[B+1]*/,
                                                                 const int32_t* __restrict__ n_keep /*[B] or null*/,
-                                                                float* __restrict__ out /*[B, d]*/) {
+                                                                float* __restrict__ out /*[B, d]*/, float scale,
+                                                                int accumulate) {
+  // out = (accumulate ? out : 0) + scale * mean: the mean (or weighted sum) over selected hidden states commutes with
+  // the mean over frames, so a pooled-only caller never materialises the [sum_T, d] average (emit_hidden).
   __shared__ float4 red[8][32];
   const int b = blockIdx.y;
   const int c = blockIdx.x * 128 + (threadIdx.x & 31) * 4;
@@ -529,8 +531,14 @@ __global__ void __launch_bounds__(256) masked_mean_pool_kernel(const float* __re
     for (int w = 1; w < 8; ++w) {
       a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
     }
-    const float inv = 1.f / (float)max(n, 1);
-    *reinterpret_cast<float4*>(out + (int64_t)b * d + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    const float inv = scale / (float)max(n, 1);
+    float4* o = reinterpret_cast<float4*>(out + (int64_t)b * d + c);
+    float4 r = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    if (accumulate) {
+      const float4 prev = *o;
+      r.x += prev.x; r.y += prev.y; r.z += prev.z; r.w += prev.w;
+    }
+    *o = r;
   }
 }
 

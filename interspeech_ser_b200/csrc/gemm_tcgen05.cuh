@@ -109,7 +109,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
 //   n0     : first column (within the group) of the warp's column range
 //   ready  : mbarrier (and parity) signalled when the accumulator is complete.
 //
-// Measured with per-tile clock stamps (tests/trace_gemm.py): the epilogue is bound by on-chip traffic, not by
+// Measured with per-tile clock stamps (tools/trace_gemm.py): the epilogue is bound by on-chip traffic, not by
 // instructions — TMEM reads (~64 B/clk/SM) plus the shared-memory transpose. Two paths keep it below the
 // K = 1024 mainloop (~10 k cycles per 128 x 256 accumulator):
 //   * bf16-only outputs (QKV, FC1, conv layers): bias + GELU are applied in the row-per-thread layout tcgen05.ld

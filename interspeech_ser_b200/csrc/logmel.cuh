@@ -55,7 +55,7 @@ struct LogmelTables {
 //   0: ce_even[n] = e[n] + e[200-n]   1: ce_odd[n] = e[n] - e[200-n]      (e[n] = xw[n] + xw[400-n])
 //   2: so_even[n] = o[n] - o[200-n]   3: so_odd[n]  = o[n] + o[200-n]     (o[n] = xw[n] - xw[400-n])
 // for n = 1..99; the n = 0 rows hold the specials xw[0], xw[200], e[100], o[100]
-__global__ void __launch_bounds__(LM_THREADS) logmel_power_kernel(const float* __restrict__ wav,
+__global__ void __launch_bounds__(LM_THREADS) logmel_power_kernel(const void* __restrict__ wav, int wav_i16,
                                                                    const UttSpan* __restrict__ utts,
                                                                    const LogmelTables tb, float* __restrict__ out,
                                                                    uint32_t* __restrict__ umax /*[B], ordered*/) {
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(LM_THREADS) logmel_power_kernel(const float* _
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * LM_FR;
   const int tid = threadIdx.x;
-  const float* x = wav + utts[b].sample_start;
+  const int64_t x0 = utts[b].sample_start;
   const int n_valid = min(utts[b].sample_len, LM_NSAMP);  // truncation; beyond n_valid the padded signal is 0
 
   for (int i = tid; i < LM_NFFT; i += LM_THREADS) s_hann[i] = tb.hann[i];
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(LM_THREADS) logmel_power_kernel(const float* _
     int s = base + i;
     if (s < 0) s = -s;
     if (s >= LM_NSAMP) s = 2 * (LM_NSAMP - 1) - s;
-    s_xp[i] = (s >= 0 && s < n_valid) ? x[s] : 0.f;
+    s_xp[i] = (s >= 0 && s < n_valid) ? load_sample(wav, wav_i16, x0 + s) : 0.f;
   }
   __syncthreads();
 

@@ -8,7 +8,7 @@
 //
 //   * the activation SLAB  [256 + taps - 1 rows] x [cg_pad channels]  is loaded ONCE (TMA, 128B swizzle, 64-channel
 //     panels); tap t, row half hf reads it through a UMMA descriptor whose start address is simply shifted by
-//     (128 hf + t) rows = (128 hf + t) * 128 B. Measured (tests/diag_posconv.py): the 128B swizzle is a function of
+//     (128 hf + t) rows = (128 hf + t) * 128 B. Measured (tools/diag_posconv.py): the 128B swizzle is a function of
 //     the absolute shared-memory address on both the TMA and the UMMA side, so a 128B-aligned (not 1024B-aligned)
 //     start address needs NO base-offset field - setting (address >> 7) & 7 there gives wrong data;
 //   * only the weights stream: one [BN x 64] K-block per (tap, channel block) through a TMA ring, each used for BOTH

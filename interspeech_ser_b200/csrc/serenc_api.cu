@@ -15,7 +15,10 @@
 #include <string>
 #include <vector>
 
+#ifdef SERENC_AB_ARMS   // development build only: the first-generation mma.sync attention and the getenv kernel switches
 #include "attention.cuh"
+#endif
+#include "attention_params.cuh"
 #include "attention_tc.cuh"
 #include "attention_tc_wide.cuh"
 #include "common.cuh"
@@ -31,6 +34,7 @@ using namespace serenc;
 // =================================================================================================
 namespace {
 thread_local char g_err[1024] = "";
+thread_local int g_cuda_err = 0;   // last cudaError_t seen by SERENC_CUDA_OK on this thread
 }
 namespace serenc {
 void set_error(const char* fmt, ...) {
@@ -39,6 +43,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+void note_cuda_error(int e) { g_cuda_err = e; }
 }  // namespace serenc
 
 #define SERENC_FAIL(code, ...)   \
@@ -105,15 +110,23 @@ struct serenc_handle {
   std::mutex mu;
   std::map<std::array<uint64_t, 8>, CUtensorMap> tmaps;
 
+  // sticky-fault state (include/serenc.h "kernel faults are sticky")
+  std::atomic<int> poisoned{0};
+  char poison_msg[512] = "";
+
+  // text encoder (SERENC_ARCH_TEXT): embedding tables, fp32
+  float *emb_word = nullptr, *emb_pos = nullptr, *emb_type = nullptr;
+
   // launch accounting / optional per-class device timing (bench.py's roofline numbers)
   std::atomic<long long> launches{0};
   bool prof = false;
   long long* gemm_trace = nullptr;  // debug: device buffer for per-tile clock stamps of the CTA-pair GEMM (serenc_debug_gemm_trace)
-  bool force_1cta = false;   // SERENC_FORCE_1CTA=1: bypass the CTA-pair GEMM (bring-up / A-B comparisons)
-  bool no_posconv_slab = false;   // SERENC_NO_POSCONV_SLAB=1: positional conv through the generic implicit GEMM
+  // A/B switches: constant false in the production build; read from the environment only with -DSERENC_AB_ARMS
+  bool force_1cta = false;        // bypass the CTA-pair GEMM
+  bool no_posconv_slab = false;   // positional conv through the generic implicit GEMM
+  bool force_mma_sync_attn = false;  // attention on the mma.sync kernel
+  int attn_deep64 = 0;               // bias-free head_dim-64 attention on the deep-pipelined kernel
   int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
-  bool force_mma_sync_attn = false;  // SERENC_ATTN_MMA_SYNC=1: attention on the mma.sync kernel (A/B arm)
-  int attn_deep64 = 0;               // SERENC_ATTN_DEEP64=1: bias-free head_dim-64 attention on the deep-pipelined kernel
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
 };
@@ -148,6 +161,39 @@ struct ProfScope {
 }  // namespace
 
 namespace {
+
+// CUDA errors that invalidate the context: every later CUDA call returns them again, so the handle is useless.
+bool cuda_error_is_sticky(int e) {
+  switch ((cudaError_t)e) {
+    case cudaErrorIllegalAddress: case cudaErrorLaunchFailure: case cudaErrorIllegalInstruction:
+    case cudaErrorMisalignedAddress: case cudaErrorInvalidAddressSpace: case cudaErrorInvalidPc:
+    case cudaErrorHardwareStackError: case cudaErrorAssert: case cudaErrorLaunchTimeout:
+    case cudaErrorECCUncorrectable: case cudaErrorUnknown: case cudaErrorDevicesUnavailable:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// Every entry point that takes a handle runs through this: a poisoned handle answers immediately, and a sticky CUDA
+// error seen by the body poisons it.
+template <typename F>
+int guarded(serenc_handle* h, F&& body) {
+  if (h && h->poisoned.load()) {
+    serenc::set_error("handle is poisoned by an earlier CUDA fault: %s", h->poison_msg);
+    return SERENC_ERR_CUDA;
+  }
+  g_cuda_err = 0;
+  const int rc = body();
+  if (rc == SERENC_ERR_CUDA && h && cuda_error_is_sticky(g_cuda_err)) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->poisoned.load()) {
+      snprintf(h->poison_msg, sizeof(h->poison_msg), "%s", g_err);
+      h->poisoned.store(1);
+    }
+  }
+  return rc;
+}
 
 template <typename T>
 int dev_alloc(serenc_handle* h, T** out, size_t count, bool zero = true) {
@@ -441,11 +487,7 @@ int launch_posconv_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   const double flops = c.alg_flops >= 0 ? c.alg_flops : 2.0 * (double)c.M * c.n_per_group * c.groups * p.num_kb * GEMM_BK;
   const double bytes = 2.0 * ((double)c.M * c.a_cols + (double)c.w_rows * p.num_kb * GEMM_BK) +
                        (double)c.M * c.n_per_group * c.groups * ((c.out_f32 ? 4 : 0) + (c.out_bf16 ? 2 : 0) + (c.resid ? 4 : 0));
-  static bool attr_set = false;   // opt-in shared memory once per process and instantiation
-  if (!attr_set) {
-    SERENC_CUDA_OK(cudaFuncSetAttribute(posconv_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
-    attr_set = true;
-  }
+  // (the opt-in to > 48 KB of dynamic shared memory is per device: serenc_create sets it for both instantiations)
   ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
   posconv_tcgen05_kernel<BN><<<grid, GEMM_THREADS, S::bytes(cfg), st>>>(tA, tW, p, cfg);
   SERENC_CUDA_OK(cudaGetLastError());
@@ -532,6 +574,7 @@ bool ln_width_ok(int cols) {
 // ---------------------------------------------------------------------------------------------
 // attention launch
 // ---------------------------------------------------------------------------------------------
+#ifdef SERENC_AB_ARMS
 template <int HD>
 int launch_attn_hd(const AttnParams& p, bool wavlm, int tmax, int heads, int batch, cudaStream_t st) {
   const dim3 grid(ceil_div(tmax, ATT_BM), heads, batch), block(ATT_THREADS);
@@ -542,6 +585,7 @@ int launch_attn_hd(const AttnParams& p, bool wavlm, int tmax, int heads, int bat
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
+#endif
 int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int batch, int64_t sum_rows, double alg_flops,
                 cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
@@ -590,14 +634,18 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
+#ifdef SERENC_AB_ARMS
   switch (h->head_dim) {
     case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
     case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
     case 120: return launch_attn_hd<120>(p, wavlm, tmax, h->cfg.heads, batch, st);
   }
-  SERENC_FAIL(SERENC_ERR_INVALID, "attention: unsupported head_dim %d", h->head_dim);
+#endif
+  SERENC_FAIL(SERENC_ERR_INVALID, "attention: head_dim %d %s the gated relative position bias is not supported", h->head_dim,
+              wavlm ? "with" : "without");
 }
 
+#ifdef SERENC_AB_ARMS
 template <int HD>
 int set_attn_attr() {
   SERENC_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -606,6 +654,7 @@ int set_attn_attr() {
                                       AttnCfg<HD>::SMEM_BYTES));
   return 0;
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // workspace carving
@@ -666,6 +715,7 @@ __global__ void whisper_plan_kernel(int batch, int32_t* __restrict__ map1 /*[B*3
 int check_ready(serenc_handle* h, int arch) {
   if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
   if (!h->finalized) SERENC_FAIL(SERENC_ERR_STATE, "handle not finalized (call serenc_finalize after loading tensors)");
+  if (h->poisoned.load()) SERENC_FAIL(SERENC_ERR_CUDA, "handle is poisoned by an earlier CUDA fault: %s", h->poison_msg);
   if (arch >= 0 && h->cfg.arch != arch) SERENC_FAIL(SERENC_ERR_INVALID, "entry point does not match the handle's architecture");
   SERENC_CUDA_OK(cudaSetDevice(h->device));
   return 0;
@@ -707,6 +757,18 @@ extern "C" int serenc_debug_gemm_trace(serenc_handle* h, void* dev_buf) {
   if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
   h->gemm_trace = reinterpret_cast<long long*>(dev_buf);
   return 0;
+}
+
+extern "C" int serenc_is_poisoned(const serenc_handle* h) { return h && h->poisoned.load() ? 1 : 0; }
+
+extern "C" int serenc_sync(serenc_handle* h, void* stream) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  return guarded(h, [&]() -> int {
+    SERENC_CUDA_OK(cudaSetDevice(h->device));
+    SERENC_CUDA_OK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+    SERENC_CUDA_OK(cudaGetLastError());
+    return 0;
+  });
 }
 
 extern "C" int64_t serenc_launch_count(const serenc_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
@@ -764,10 +826,12 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
   h->head_dim = hd;
+#ifdef SERENC_AB_ARMS
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_DEEP64"); if (e) h->attn_deep64 = e[0] == '1'; }
+#endif
   *out = h;
 
   int st = 0;
@@ -807,6 +871,13 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     A(&h->wc2, (size_t)d * 3 * d); A(&h->bc2, d);
     A(&h->pos_emb, (size_t)cfg->max_source_positions * d);
     if (cfg->max_source_positions != 1500 || d % 64) { st = SERENC_ERR_INVALID; serenc::set_error("whisper: max_source_positions must be 1500"); }
+  } else if (cfg->arch == SERENC_ARCH_TEXT) {
+    if (hd != 64 || cfg->vocab_size < 1 || cfg->max_positions < 2 || cfg->type_vocab_size < 1 || cfg->pad_token_id < 0 ||
+        cfg->pad_token_id >= cfg->max_positions) {
+      st = SERENC_ERR_INVALID; serenc::set_error("text encoder: head_dim must be 64 and vocab / position / type sizes positive");
+    } else {
+      A(&h->emb_word, (size_t)cfg->vocab_size * d); A(&h->emb_pos, (size_t)cfg->max_positions * d); A(&h->emb_type, (size_t)cfg->type_vocab_size * d);
+    }
   } else {
     st = SERENC_ERR_INVALID;
     serenc::set_error("unknown arch %d", cfg->arch);
@@ -819,12 +890,16 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+#ifdef SERENC_AB_ARMS
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
+#endif
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
+    attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
   }
   if (st) {
     serenc_destroy(h);
@@ -949,6 +1024,9 @@ extern "C" int serenc_load_tensor(serenc_handle* h, const char* name, const floa
     st = upload_bf16(h->wc2, pack_conv(data, d, d, 3, d));
   } else if (c.arch == SERENC_ARCH_WHISPER && nm == "conv2.bias") { SERENC_TRY(expect(d)); st = upload_f32(h->bc2, data, n); }
   else if (c.arch == SERENC_ARCH_WHISPER && nm == "embed_positions") { SERENC_TRY(expect((int64_t)c.max_source_positions * d)); st = upload_f32(h->pos_emb, data, n); }
+  else if (c.arch == SERENC_ARCH_TEXT && nm == "embed.word") { SERENC_TRY(expect((int64_t)c.vocab_size * d)); st = upload_f32(h->emb_word, data, n); }
+  else if (c.arch == SERENC_ARCH_TEXT && nm == "embed.position") { SERENC_TRY(expect((int64_t)c.max_positions * d)); st = upload_f32(h->emb_pos, data, n); }
+  else if (c.arch == SERENC_ARCH_TEXT && nm == "embed.type") { SERENC_TRY(expect((int64_t)c.type_vocab_size * d)); st = upload_f32(h->emb_type, data, n); }
   else if (c.arch == SERENC_ARCH_WHISPER && nm == "mel_filters") {
     SERENC_TRY(expect((int64_t)LM_BINS * c.n_mels));
     h->mel_filters_host.assign(data, data + n);
@@ -971,7 +1049,7 @@ extern "C" int serenc_finalize(serenc_handle* h) {
     static const char* per[] = {"ln1.weight", "ln1.bias", "ln2.weight", "ln2.bias", "q.weight", "q.bias", "k.weight",
                                 "v.weight", "v.bias", "o.weight", "o.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"};
     for (const char* s : per) { snprintf(buf, sizeof(buf), "layer%d.%s", i, s); req.push_back(buf); }
-    if (c.arch == SERENC_ARCH_W2V) { snprintf(buf, sizeof(buf), "layer%d.k.bias", i); req.push_back(buf); }  // Whisper's k_proj has no bias
+    if (c.arch != SERENC_ARCH_WHISPER) { snprintf(buf, sizeof(buf), "layer%d.k.bias", i); req.push_back(buf); }  // Whisper's k_proj has no bias
     if (c.wavlm_rel_bias) {
       for (const char* s : {"gru.weight", "gru.bias", "gru.const"}) { snprintf(buf, sizeof(buf), "layer%d.%s", i, s); req.push_back(buf); }
     }
@@ -989,6 +1067,8 @@ extern "C" int serenc_finalize(serenc_handle* h) {
     for (const char* s : {"featproj.weight", "featproj.bias", "posconv.weight", "posconv.bias"}) req.push_back(s);
     if (!c.no_feat_proj_ln) { req.push_back("featproj.ln.weight"); req.push_back("featproj.ln.bias"); }
     if (c.wavlm_rel_bias) req.push_back("rel_attn_embed");
+  } else if (c.arch == SERENC_ARCH_TEXT) {
+    for (const char* s : {"embed.word", "embed.position", "embed.type"}) req.push_back(s);
   } else {
     for (const char* s : {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "embed_positions", "mel_filters"}) req.push_back(s);
   }
@@ -1055,7 +1135,9 @@ struct EmitCtx {
   bool first = true;
   float* frames_out;
   float* pooled_out;
-  float* acc;  // REDUCE_MEAN accumulator ([sumT, d]); == frames_out when that is given
+  float* acc;  // REDUCE_MEAN / _WEIGHTED accumulator ([sumT, d]); == frames_out when that is given
+  const float* weights = nullptr;   // host [n_sel]: SERENC_REDUCE_WEIGHTED; nullptr = 1 / n_sel each (the mean)
+  bool pooled_linear = false;       // reducing, pooled output only: every selected state is pooled straight into pooled_out
   int64_t sumT;
   int d;
   int batch;
@@ -1063,10 +1145,11 @@ struct EmitCtx {
   const int32_t* n_keep_dev;
 };
 
-int pool_launch(serenc_handle* h, const float* x, int64_t sumT, int d, int batch, const int32_t* foff, const int32_t* n_keep, float* out, cudaStream_t st) {
+int pool_launch(serenc_handle* h, const float* x, int64_t sumT, int d, int batch, const int32_t* foff, const int32_t* n_keep, float* out, cudaStream_t st,
+                float scale = 1.f, int accumulate = 0) {
   const dim3 grid(ceil_div(d, 128), batch);
   ProfScope ps(h, SERENC_PROF_POOL, 1, 0.0, (double)sumT * d * 4 + (double)batch * d * 4, st);
-  masked_mean_pool_kernel<<<grid, 256, 0, st>>>(x, d, foff, n_keep, out);
+  masked_mean_pool_kernel<<<grid, 256, 0, st>>>(x, d, foff, n_keep, out, scale, accumulate);
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1080,10 +1163,16 @@ int emit_hidden(serenc_handle* h, EmitCtx& e, int idx, const float* src, cudaStr
     if (e.pooled_out)
       SERENC_TRY(pool_launch(h, src, e.sumT, e.d, e.batch, e.frame_off_dev, e.n_keep_dev, e.pooled_out + (int64_t)e.sel * e.batch * e.d, st));
   } else {
-    const int64_t n4 = n / 4;
-    ProfScope ps(h, SERENC_PROF_POOL, 1, 0.0, (double)n * (e.first ? 8 : 12), st);
-    accum_scaled_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(e.acc, src, n4, 1.0f / (float)e.n_sel, e.first ? 1 : 0);
-    SERENC_CUDA_OK(cudaGetLastError());
+    const float wgt = e.weights ? e.weights[e.sel] : 1.0f / (float)e.n_sel;
+    if (e.pooled_linear) {
+      // mean over layers and mean over frames commute: one read of the hidden state, no [sum_T, d] accumulator traffic
+      SERENC_TRY(pool_launch(h, src, e.sumT, e.d, e.batch, e.frame_off_dev, e.n_keep_dev, e.pooled_out, st, wgt, e.first ? 0 : 1));
+    } else {
+      const int64_t n4 = n / 4;
+      ProfScope ps(h, SERENC_PROF_POOL, 1, 0.0, (double)n * (e.first ? 8 : 12), st);
+      accum_scaled_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(e.acc, src, n4, wgt, e.first ? 1 : 0);
+      SERENC_CUDA_OK(cudaGetLastError());
+    }
     e.first = false;
   }
   e.sel++;
@@ -1098,6 +1187,7 @@ struct StackBufs {
   bf16* att;    // [sumT, d]
   bf16* ffn;    // [sumT, ffn]
   float* gate = nullptr;  // [sumT, heads] WavLM gate of the current layer
+  const int32_t* key_len = nullptr;  // [batch] text encoder: keys (non-pad tokens) per sequence; nullptr = every row is a key
 };
 
 // gate of layer li's attention, to be produced by the LayerNorm that writes its input (tcgen05 attention path only)
@@ -1131,7 +1221,7 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
       AttnParams p;
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
-      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate; p.key_len = b.key_len;
       p.gate_ready = lg.out != nullptr;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
@@ -1155,7 +1245,7 @@ int run_stack(serenc_handle* h, const StackBufs& b, int64_t sumT, int batch, int
   }
   SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.xf, d, h->fin_g, h->fin_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st)));
   SERENC_TRY(emit_hidden(h, e, c.layers, b.xf, st));
-  if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
+  if (e.reduce != SERENC_REDUCE_NONE && e.pooled_out && e.n_sel > 0 && !e.pooled_linear)
     SERENC_TRY(pool_launch(h, e.acc, sumT, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
   return 0;
 }
@@ -1182,7 +1272,7 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
       AttnParams p;
       p.qkv = b.qkv; p.ld_qkv = 3 * d; p.d = d; p.frame_off = frame_off_dev; p.out = b.att;
       p.scale = 1.0f / sqrtf((float)h->head_dim);
-      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate;
+      p.hln = b.hln; p.gru_w = l.gru_w; p.gru_b = l.gru_b; p.gru_const = l.gru_const; p.btab = h->btab; p.gate = b.gate; p.key_len = b.key_len;
       p.gate_ready = ln_gate_for(h, b, li).out != nullptr;
       SERENC_TRY(launch_attn(h, p, c.wavlm_rel_bias != 0, tmax, batch, sumT, attn_flops, st));
     }
@@ -1205,12 +1295,26 @@ int run_stack_post_ln(serenc_handle* h, const StackBufs& b, int64_t sumT, int ba
     SERENC_TRY((launch_ln_t<float, float, false>(h, b.x, d, b.x, d, l.ln2_g, l.ln2_b, sumT, d, nullptr, nullptr, c.layer_norm_eps, st, b.hln, ln_gate_for(h, b, li + 1))));
     SERENC_TRY(emit_hidden(h, e, li + 1, b.x, st));
   }
-  if (e.reduce == SERENC_REDUCE_MEAN && e.pooled_out && e.n_sel > 0)
+  if (e.reduce != SERENC_REDUCE_NONE && e.pooled_out && e.n_sel > 0 && !e.pooled_linear)
     SERENC_TRY(pool_launch(h, e.acc, sumT, d, batch, frame_off_dev, e.n_keep_dev, e.pooled_out, st));
   return 0;
 }
 
 int popcount64(uint64_t v) { int n = 0; while (v) { n += (int)(v & 1); v >>= 1; } return n; }
+
+int make_emit(EmitCtx* e, uint64_t layer_mask, int reduce, const float* layer_weights, float* frames_out, float* pooled_out,
+              float* acc_ws, int64_t sumT, int d, int batch, const int32_t* foff_dev, const int32_t* n_keep_dev) {
+  if (reduce != SERENC_REDUCE_NONE && reduce != SERENC_REDUCE_MEAN && reduce != SERENC_REDUCE_WEIGHTED)
+    SERENC_FAIL(SERENC_ERR_INVALID, "unknown reduce mode %d", reduce);
+  if (reduce == SERENC_REDUCE_WEIGHTED && !layer_weights) SERENC_FAIL(SERENC_ERR_INVALID, "SERENC_REDUCE_WEIGHTED needs layer_weights");
+  e->mask = layer_mask; e->reduce = reduce; e->n_sel = popcount64(layer_mask);
+  e->weights = reduce == SERENC_REDUCE_WEIGHTED ? layer_weights : nullptr;
+  e->frames_out = frames_out; e->pooled_out = pooled_out;
+  e->acc = (reduce != SERENC_REDUCE_NONE && frames_out) ? frames_out : acc_ws;
+  e->pooled_linear = reduce != SERENC_REDUCE_NONE && !frames_out && pooled_out;
+  e->sumT = sumT; e->d = d; e->batch = batch; e->frame_off_dev = foff_dev; e->n_keep_dev = n_keep_dev;
+  return 0;
+}
 
 // ---- wav2vec2-family plan ----
 struct W2VPlan {
@@ -1381,8 +1485,14 @@ extern "C" int serenc_w2v_workspace_bytes(const serenc_handle* h, const int32_t*
   return 0;
 }
 
+static int wav_normalize_impl(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                              int batch, float* out_dev, int64_t out_stride, int32_t out_len, void* stream);
 extern "C" int serenc_wav_normalize(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
                                     int batch, float* out_dev, int64_t out_stride, int32_t out_len, void* stream) {
+  return guarded(h, [&] { return wav_normalize_impl(h, wav_dev, sample_start, sample_len, batch, out_dev, out_stride, out_len, stream); });
+}
+static int wav_normalize_impl(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                              int batch, float* out_dev, int64_t out_stride, int32_t out_len, void* stream) {
   SERENC_TRY(check_ready(h, -1));
   if (!wav_dev || !sample_start || !sample_len || !out_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1392,7 +1502,7 @@ extern "C" int serenc_wav_normalize(serenc_handle* h, const float* wav_dev, cons
   UttSpan* d_utts = reinterpret_cast<UttSpan*>(dscratch);
   float2* d_stats = reinterpret_cast<float2*>(d_utts + batch);
   SERENC_TRY(upload_spans(sample_start, sample_len, batch, d_utts, st));
-  wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, d_utts, d_stats);
+  wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, 0, d_utts, d_stats);
   SERENC_CUDA_OK(cudaGetLastError());
   const dim3 grid(ceil_div(out_len, 1024) < 64 ? ceil_div(out_len, 1024) : 64, batch);
   wav_normalize_kernel<<<grid, 256, 0, st>>>(wav_dev, d_utts, d_stats, out_dev, out_stride, out_len);
@@ -1401,12 +1511,24 @@ extern "C" int serenc_wav_normalize(serenc_handle* h, const float* wav_dev, cons
   return 0;
 }
 
-extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
-                                 int batch, int normalize, uint64_t layer_mask, int reduce, float* frames_out_dev,
-                                 float* pooled_out_dev, int64_t* frame_offsets_out, void* workspace_dev, size_t workspace_bytes,
-                                 void* stream) {
+static int encode_w2v_impl(serenc_handle* h, const serenc_w2v_call& a) {
   SERENC_TRY(check_ready(h, SERENC_ARCH_W2V));
+  const void* wav_dev = a.wav_dev;
+  const int64_t* sample_start = a.sample_start;
+  const int32_t* sample_len = a.sample_len;
+  const int batch = a.batch, normalize = a.normalize, reduce = a.reduce;
+  uint64_t layer_mask = a.layer_mask;
+  float* frames_out_dev = a.frames_out_dev;
+  float* pooled_out_dev = a.pooled_out_dev;
+  int64_t* frame_offsets_out = a.frame_offsets_out;
+  void* workspace_dev = a.workspace_dev;
+  const size_t workspace_bytes = a.workspace_bytes;
+  void* stream = a.stream;
   if (!wav_dev || !sample_start || !sample_len || !workspace_dev) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  if (a.wav_dtype != SERENC_WAV_F32 && a.wav_dtype != SERENC_WAV_I16) SERENC_FAIL(SERENC_ERR_INVALID, "unknown wav_dtype %d", a.wav_dtype);
+  const int wav_i16 = a.wav_dtype == SERENC_WAV_I16;
+  if (a.extract_features_out_dev && h->cfg.no_feat_proj_ln)
+    SERENC_FAIL(SERENC_ERR_INVALID, "extract_features needs a feature-projection LayerNorm (HubertModel returns none)");
   const serenc_config& c = h->cfg;
   const int d = c.hidden, C = c.conv_dim;
   if (c.layers < 63) layer_mask &= ((1ull << (c.layers + 1)) - 1);
@@ -1453,7 +1575,7 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
       double nsamp = 0;
       for (int b = 0; b < batch; ++b) nsamp += sample_len[b];
       ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, 8.0 * nsamp, st);
-      wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, w.utts, w.stats);
+      wav_stats_kernel<<<batch, 1024, 0, st>>>(wav_dev, wav_i16, w.utts, w.stats);
       SERENC_CUDA_OK(cudaGetLastError());
     }
     int slot_max = 0;
@@ -1464,17 +1586,17 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     const float2* stp = normalize ? w.stats : nullptr;
     const float* b0 = c.conv_bias ? h->conv_b[0] : nullptr;
     if (!c.conv_group_norm) {
-      ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, 4.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
-      conv0_kernel<0><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, h->conv_g[0], h->conv_be[0], w.cbuf0, nullptr, nullptr, 0);
+      ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, (wav_i16 ? 2.0 : 4.0) * nsamp0 + 2.0 * t0sum * CONV0_C, st);
+      conv0_kernel<0><<<grid, 256, 0, st>>>(wav_dev, wav_i16, w.utts, stp, h->conv0_w, b0, h->conv_g[0], h->conv_be[0], w.cbuf0, nullptr, nullptr, 0);
       SERENC_CUDA_OK(cudaGetLastError());
     } else {
       // GroupNorm(512 groups) on conv0: statistics over each utterance's valid frames, then recompute + apply
       ProfScope ps(h, SERENC_PROF_CONV0, 3, 4.0 * t0sum * CONV0_C * CONV0_K, 8.0 * nsamp0 + 2.0 * t0sum * CONV0_C, st);
-      conv0_kernel<1><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, w.gn_partial, nullptr, w.gn_tiles);
+      conv0_kernel<1><<<grid, 256, 0, st>>>(wav_dev, wav_i16, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, w.gn_partial, nullptr, w.gn_tiles);
       SERENC_CUDA_OK(cudaGetLastError());
       conv0_gn_finalize_kernel<<<dim3(CONV0_C / 128, batch), 128, 0, st>>>(w.gn_partial, w.utts, w.gn_tiles, h->conv_g[0], h->conv_be[0], w.gn_affine);
       SERENC_CUDA_OK(cudaGetLastError());
-      conv0_kernel<2><<<grid, 256, 0, st>>>(wav_dev, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, nullptr, w.gn_affine, w.gn_tiles);
+      conv0_kernel<2><<<grid, 256, 0, st>>>(wav_dev, wav_i16, w.utts, stp, h->conv0_w, b0, nullptr, nullptr, w.cbuf0, nullptr, w.gn_affine, w.gn_tiles);
       SERENC_CUDA_OK(cudaGetLastError());
     }
   }
@@ -1495,7 +1617,11 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
     bf16* t = cin; cin = cout; cout = t;
   }
   // ---- feature projection: LN(512) over the valid frames (gathered into the packed layout) -> Linear(512 -> d) ----
-  if (!c.no_feat_proj_ln) {
+  if (!c.no_feat_proj_ln && a.extract_features_out_dev) {
+    // HF's `extract_features` (the normed 512-d features, modeling_wavlm.py:93-105) in fp32 + the bf16 GEMM operand
+    SERENC_TRY((launch_ln_t<bf16, float, false>(h, cin, C, a.extract_features_out_dev, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr,
+                                                c.layer_norm_eps, st, w.featln)));
+  } else if (!c.no_feat_proj_ln) {
     SERENC_TRY((launch_ln_t<bf16, bf16, false>(h, cin, C, w.featln, C, h->fp_g, h->fp_be, p.sumT, C, w.fp_gather, nullptr, c.layer_norm_eps, st)));
   } else {
     ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, (double)p.sumT * C * 4, st);
@@ -1529,10 +1655,7 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   }
   // ---- transformer stack ----
   EmitCtx e;
-  e.mask = layer_mask; e.reduce = reduce; e.n_sel = popcount64(layer_mask);
-  e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
-  e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
-  e.sumT = p.sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = nullptr;
+  SERENC_TRY(make_emit(&e, layer_mask, reduce, a.layer_weights, frames_out_dev, pooled_out_dev, w.acc, p.sumT, d, batch, w.foff, nullptr));
   double attn_flops = 0.0;
   for (int b = 0; b < batch; ++b) attn_flops += 4.0 * (double)p.T[6][b] * p.T[6][b] * d;
   if (c.post_layer_norm) SERENC_TRY(run_stack_post_ln(h, w.sb, p.sumT, batch, p.tmax, w.foff, attn_flops, e, st));
@@ -1540,12 +1663,29 @@ extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const i
   return 0;
 }
 
-extern "C" int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
-                                    int32_t t_max, float* out_dev, void* stream) {
+extern "C" int serenc_encode_w2v_ex(serenc_handle* h, const serenc_w2v_call* call) {
+  if (!call) SERENC_FAIL(SERENC_ERR_INVALID, "null argument");
+  return guarded(h, [&] { return encode_w2v_impl(h, *call); });
+}
+
+extern "C" int serenc_encode_w2v(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                                 int batch, int normalize, uint64_t layer_mask, int reduce, float* frames_out_dev,
+                                 float* pooled_out_dev, int64_t* frame_offsets_out, void* workspace_dev, size_t workspace_bytes,
+                                 void* stream) {
+  serenc_w2v_call a;
+  memset(&a, 0, sizeof(a));
+  a.wav_dev = wav_dev; a.wav_dtype = SERENC_WAV_F32; a.batch = batch; a.sample_start = sample_start; a.sample_len = sample_len;
+  a.normalize = normalize; a.reduce = reduce; a.layer_mask = layer_mask; a.frames_out_dev = frames_out_dev;
+  a.pooled_out_dev = pooled_out_dev; a.frame_offsets_out = frame_offsets_out; a.workspace_dev = workspace_dev;
+  a.workspace_bytes = workspace_bytes; a.stream = stream;
+  return serenc_encode_w2v_ex(h, &a);
+}
+
+static int unpack_rows_impl(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
+                            int32_t t_max, int32_t d, float* out_dev, void* stream) {
   SERENC_TRY(check_ready(h, -1));
-  if (!packed_dev || !frame_offsets || !out_dev || batch <= 0 || t_max <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  if (!packed_dev || !frame_offsets || !out_dev || batch <= 0 || t_max <= 0 || d <= 0 || d % 4) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int d = h->cfg.hidden;
   int32_t* d_off;
   SERENC_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&d_off), 4 * (size_t)(batch + 1), st));
   void* hs;
@@ -1560,13 +1700,24 @@ extern "C" int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, c
   return 0;
 }
 
+extern "C" int serenc_unpack_rows(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
+                                  int32_t t_max, int32_t cols, float* out_dev, void* stream) {
+  return guarded(h, [&] { return unpack_rows_impl(h, packed_dev, frame_offsets, batch, t_max, cols, out_dev, stream); });
+}
+extern "C" int serenc_unpack_frames(serenc_handle* h, const float* packed_dev, const int64_t* frame_offsets, int batch,
+                                    int32_t t_max, float* out_dev, void* stream) {
+  if (!h) SERENC_FAIL(SERENC_ERR_INVALID, "null handle");
+  return serenc_unpack_rows(h, packed_dev, frame_offsets, batch, t_max, h->cfg.hidden, out_dev, stream);
+}
+
 // =================================================================================================
 // Whisper
 // =================================================================================================
-extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
-                             int batch, float* mel_out_dev, void* scratch_dev, void* stream) {
+static int logmel_impl(serenc_handle* h, const void* wav_dev, int wav_dtype, const int64_t* sample_start, const int32_t* sample_len,
+                       int batch, float* mel_out_dev, void* scratch_dev, void* stream) {
   SERENC_TRY(check_ready(h, SERENC_ARCH_WHISPER));
   if (!wav_dev || !sample_start || !sample_len || !mel_out_dev || !scratch_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  if (wav_dtype != SERENC_WAV_F32 && wav_dtype != SERENC_WAV_I16) SERENC_FAIL(SERENC_ERR_INVALID, "unknown wav_dtype %d", wav_dtype);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // scratch layout: [batch] ordered-max words, then the span table
   UttSpan* d_utts = reinterpret_cast<UttSpan*>(reinterpret_cast<uint8_t*>(scratch_dev) + (((size_t)batch * 4 + 63) & ~size_t(63)));
@@ -1578,12 +1729,20 @@ extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64
   tb.mel_ptr = h->mel_ptr; tb.mel_bin = h->mel_bin; tb.mel_w = h->mel_w; tb.n_mels = h->cfg.n_mels;
   const dim3 grid(ceil_div(LM_FRAMES, LM_FR), batch);
   ProfScope ps(h, SERENC_PROF_LOGMEL, 3, 0.0, (double)batch * (4.0 * LM_NSAMP + 4.0 * h->cfg.n_mels * LM_FRAMES), st);
-  logmel_power_kernel<<<grid, LM_THREADS, 0, st>>>(wav_dev, d_utts, tb, mel_out_dev, umax);
+  logmel_power_kernel<<<grid, LM_THREADS, 0, st>>>(wav_dev, wav_dtype == SERENC_WAV_I16, d_utts, tb, mel_out_dev, umax);
   SERENC_CUDA_OK(cudaGetLastError());
   const int64_t per_utt = (int64_t)h->cfg.n_mels * LM_FRAMES;
   logmel_finalize_kernel<<<dim3(64, batch), 256, 0, st>>>(mel_out_dev, umax, per_utt);
   SERENC_CUDA_OK(cudaGetLastError());
   return 0;
+}
+extern "C" int serenc_logmel_ex(serenc_handle* h, const void* wav_dev, int wav_dtype, const int64_t* sample_start, const int32_t* sample_len,
+                                int batch, float* mel_out_dev, void* scratch_dev, void* stream) {
+  return guarded(h, [&] { return logmel_impl(h, wav_dev, wav_dtype, sample_start, sample_len, batch, mel_out_dev, scratch_dev, stream); });
+}
+extern "C" int serenc_logmel(serenc_handle* h, const float* wav_dev, const int64_t* sample_start, const int32_t* sample_len,
+                             int batch, float* mel_out_dev, void* scratch_dev, void* stream) {
+  return serenc_logmel_ex(h, wav_dev, SERENC_WAV_F32, sample_start, sample_len, batch, mel_out_dev, scratch_dev, stream);
 }
 
 namespace {
@@ -1624,9 +1783,9 @@ extern "C" int serenc_whisper_workspace_bytes(const serenc_handle* h, int batch,
   return 0;
 }
 
-extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
-                                     const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev, void* workspace_dev,
-                                     size_t workspace_bytes, void* stream) {
+static int encode_whisper_impl(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
+                               const float* layer_weights, const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev,
+                               void* workspace_dev, size_t workspace_bytes, void* stream) {
   SERENC_TRY(check_ready(h, SERENC_ARCH_WHISPER));
   if (!mel_dev || !workspace_dev || batch <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
   const serenc_config& c = h->cfg;
@@ -1686,12 +1845,137 @@ extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int
     SERENC_TRY(launch_gemm(h, g, st));
   }
   EmitCtx e;
-  e.mask = layer_mask; e.reduce = reduce; e.n_sel = popcount64(layer_mask);
-  e.frames_out = frames_out_dev; e.pooled_out = pooled_out_dev;
-  e.acc = (reduce == SERENC_REDUCE_MEAN && frames_out_dev) ? frames_out_dev : w.acc;
-  e.sumT = sumT; e.d = d; e.batch = batch; e.frame_off_dev = w.foff; e.n_keep_dev = w.n_keep;
+  SERENC_TRY(make_emit(&e, layer_mask, reduce, layer_weights, frames_out_dev, pooled_out_dev, w.acc, sumT, d, batch, w.foff, w.n_keep));
   SERENC_TRY(run_stack(h, w.sb, sumT, batch, 1500, w.foff, 4.0 * 1500.0 * 1500.0 * d * batch, e, st));
   return 0;
+}
+extern "C" int serenc_encode_whisper_ex(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
+                                        const float* layer_weights, const int32_t* n_keep, float* frames_out_dev,
+                                        float* pooled_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return guarded(h, [&] {
+    return encode_whisper_impl(h, mel_dev, batch, layer_mask, reduce, layer_weights, n_keep, frames_out_dev, pooled_out_dev, workspace_dev,
+                               workspace_bytes, stream);
+  });
+}
+extern "C" int serenc_encode_whisper(serenc_handle* h, const float* mel_dev, int batch, uint64_t layer_mask, int reduce,
+                                     const int32_t* n_keep, float* frames_out_dev, float* pooled_out_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream) {
+  return serenc_encode_whisper_ex(h, mel_dev, batch, layer_mask, reduce, nullptr, n_keep, frames_out_dev, pooled_out_dev, workspace_dev,
+                                  workspace_bytes, stream);
+}
+
+// =================================================================================================
+// text encoder (RoBERTa): embeddings + post-LN stack
+// =================================================================================================
+namespace {
+// x[row] = word[ids[row]] + position[pos_id] + type[0];  pos_id = pad + 1 + t for the valid_len leading tokens, pad after
+// (HF RobertaEmbeddings.forward + create_position_ids_from_input_ids, modeling_roberta.py). One warp per row.
+__global__ void __launch_bounds__(256) text_embed_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ valid_len,
+                                                         int seq_len, int64_t rows, int d, int vocab, int max_pos, int pad,
+                                                         const float* __restrict__ word, const float* __restrict__ pos,
+                                                         const float* __restrict__ type, float* __restrict__ x) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(row / seq_len), t = (int)(row - (int64_t)b * seq_len);
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);   // memory safety only: the host side rejects out-of-range ids
+  int pid = t < valid_len[b] ? pad + 1 + t : pad;
+  pid = pid >= max_pos ? max_pos - 1 : pid;
+  const float4* w4 = reinterpret_cast<const float4*>(word + (int64_t)id * d);
+  const float4* p4 = reinterpret_cast<const float4*>(pos + (int64_t)pid * d);
+  const float4* t4 = reinterpret_cast<const float4*>(type);
+  float4* o4 = reinterpret_cast<float4*>(x + row * d);
+  for (int c = lane; c < d / 4; c += 32) {
+    const float4 a = __ldg(w4 + c), e = __ldg(t4 + c), q = __ldg(p4 + c);
+    // HF: inputs_embeds + token_type_embeddings, then + position_embeddings
+    o4[c] = make_float4((a.x + e.x) + q.x, (a.y + e.y) + q.y, (a.z + e.z) + q.z, (a.w + e.w) + q.w);
+  }
+}
+
+struct TextWs {
+  int32_t *foff, *klen;
+  StackBufs sb; float* acc;
+  size_t bytes;
+};
+void carve_text(const serenc_handle* h, int batch, int seq_len, void* base, TextWs* w) {
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  const int64_t sumT = (int64_t)batch * seq_len;
+  Carver cv(base);
+  w->foff = cv.take<int32_t>(batch + 1);
+  w->klen = cv.take<int32_t>(batch);
+  w->sb.x = cv.take<float>((size_t)sumT * d);
+  w->sb.xf = nullptr;
+  w->sb.hln = cv.take<bf16>((size_t)sumT * d);
+  w->sb.qkv = cv.take<bf16>((size_t)sumT * 3 * d);
+  w->sb.att = cv.take<bf16>((size_t)sumT * d);
+  w->sb.ffn = cv.take<bf16>((size_t)sumT * c.ffn);
+  w->acc = cv.take<float>((size_t)sumT * d);
+  w->bytes = cv.used();
+}
+}  // namespace
+
+extern "C" int serenc_text_workspace_bytes(const serenc_handle* h, int batch, int seq_len, size_t* out_bytes) {
+  if (!h || !out_bytes || batch <= 0 || seq_len <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  if (h->cfg.arch != SERENC_ARCH_TEXT) SERENC_FAIL(SERENC_ERR_INVALID, "not a text-encoder handle");
+  TextWs w;
+  carve_text(h, batch, seq_len, nullptr, &w);
+  *out_bytes = w.bytes + 256;
+  return 0;
+}
+
+static int encode_text_impl(serenc_handle* h, const int32_t* input_ids_dev, const int32_t* valid_len, int batch, int seq_len,
+                            uint64_t layer_mask, int reduce, const float* layer_weights, float* frames_out_dev,
+                            float* pooled_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  SERENC_TRY(check_ready(h, SERENC_ARCH_TEXT));
+  if (!input_ids_dev || !valid_len || !workspace_dev || batch <= 0 || seq_len <= 0) SERENC_FAIL(SERENC_ERR_INVALID, "bad argument");
+  const serenc_config& c = h->cfg;
+  const int d = c.hidden;
+  if (seq_len + c.pad_token_id + 1 > c.max_positions)
+    SERENC_FAIL(SERENC_ERR_INVALID, "sequence length %d exceeds the position table (%d rows, first position id %d)", seq_len, c.max_positions, c.pad_token_id + 1);
+  if (c.layers < 63) layer_mask &= ((1ull << (c.layers + 1)) - 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TextWs w;
+  carve_text(h, batch, seq_len, workspace_dev, &w);
+  if (w.bytes > workspace_bytes) SERENC_FAIL(SERENC_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+  const int64_t sumT = (int64_t)batch * seq_len;
+  double attn_flops = 0.0;
+  {
+    void* hs;
+    SERENC_TRY(stage_reserve(4 * (size_t)(2 * batch + 1), &hs, st));
+    int32_t* hf = reinterpret_cast<int32_t*>(hs);
+    for (int b = 0; b <= batch; ++b) hf[b] = b * seq_len;
+    for (int b = 0; b < batch; ++b) {
+      if (valid_len[b] < 1 || valid_len[b] > seq_len)
+        SERENC_FAIL(SERENC_ERR_INVALID, "sequence %d: valid_len %d outside [1, %d]", b, (int)valid_len[b], seq_len);
+      hf[batch + 1 + b] = valid_len[b];
+      attn_flops += 4.0 * (double)seq_len * valid_len[b] * d;
+    }
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.foff, hf, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.klen, hf + batch + 1, 4 * (size_t)batch, cudaMemcpyHostToDevice, st));
+    SERENC_TRY(stage_commit(st));
+  }
+  {
+    ProfScope ps(h, SERENC_PROF_MISC, 1, 0.0, (double)sumT * d * 12, st);
+    text_embed_kernel<<<(unsigned)ceil_div64(sumT, 8), 256, 0, st>>>(input_ids_dev, w.klen, seq_len, sumT, d, c.vocab_size, c.max_positions,
+                                                                    c.pad_token_id, h->emb_word, h->emb_pos, h->emb_type, w.sb.x);
+    SERENC_CUDA_OK(cudaGetLastError());
+  }
+  w.sb.key_len = w.klen;
+  EmitCtx e;
+  SERENC_TRY(make_emit(&e, layer_mask, reduce, layer_weights, frames_out_dev, pooled_out_dev, w.acc, sumT, d, batch, w.foff, w.klen));
+  // RobertaEmbeddings.LayerNorm is the stack's leading LayerNorm (loaded as final_ln.*); RobertaLayer is post-LN
+  SERENC_TRY(run_stack_post_ln(h, w.sb, sumT, batch, seq_len, w.foff, attn_flops, e, st));
+  return 0;
+}
+extern "C" int serenc_encode_text(serenc_handle* h, const int32_t* input_ids_dev, const int32_t* valid_len, int batch, int seq_len,
+                                  uint64_t layer_mask, int reduce, const float* layer_weights, float* frames_out_dev,
+                                  float* pooled_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return guarded(h, [&] {
+    return encode_text_impl(h, input_ids_dev, valid_len, batch, seq_len, layer_mask, reduce, layer_weights, frames_out_dev, pooled_out_dev,
+                            workspace_dev, workspace_bytes, stream);
+  });
 }
 
 // =================================================================================================

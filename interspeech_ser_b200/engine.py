@@ -4,16 +4,26 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+from collections import OrderedDict
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib
-from .configs import ARCH_WHISPER, ARCH_W2V, EncoderConfig, w2v_num_frames
+from .configs import ARCH_TEXT, ARCH_WHISPER, ARCH_W2V, EncoderConfig, w2v_num_frames
 
 REDUCE_NONE = 0
 REDUCE_MEAN = 1
+REDUCE_WEIGHTED = 2   # sum_i w_i * hidden_states[sel_i] (lora_wavlm/model.py:164-181 of the reference)
+
+
+def _wav_dtype(wav: torch.Tensor) -> int:
+    if wav.dtype == torch.float32:
+        return _lib.WAV_F32
+    if wav.dtype == torch.int16:
+        return _lib.WAV_I16
+    raise TypeError(f"waveforms must be float32 or int16 PCM, got {wav.dtype}")
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -53,7 +63,7 @@ class UploadRing:
         self._i = 0
 
     def upload(self, host: torch.Tensor) -> Tuple[torch.Tensor, int]:
-        assert host.dtype == torch.float32 and host.dim() == 1 and not host.is_cuda
+        assert host.dtype in (torch.float32, torch.int16, torch.int32) and host.dim() == 1 and not host.is_cuda
         if not host.is_pinned():
             host = host.pin_memory()
         s = self._i % len(self._bufs)
@@ -61,8 +71,12 @@ class UploadRing:
         n = host.numel()
         cur = torch.cuda.current_stream(self.device)
         buf = self._bufs[s]
+        if buf is not None and buf.dtype != host.dtype:    # the slot is a byte pool: re-typed views, no new allocation
+            nb = buf.numel() * buf.element_size()
+            buf = buf.view(torch.uint8)[: nb - nb % host.element_size()].view(host.dtype)
+            self._bufs[s] = buf
         if buf is None or buf.numel() < n:
-            buf = torch.empty(max(n, 1), dtype=torch.float32, device=self.device)   # allocated on the compute stream ...
+            buf = torch.empty(max(n, 1), dtype=host.dtype, device=self.device)   # allocated on the compute stream ...
             buf.record_stream(self.copy_stream)                                       # ... and written on the copy stream
             self._bufs[s] = buf
             self.copy_stream.wait_stream(cur)    # the allocator may hand back memory the compute stream is still using
@@ -148,6 +162,8 @@ class Engine:
         c.conv_group_norm = int(cfg.feat_extract_norm == "group")
         c.post_layer_norm = int(not cfg.do_stable_layer_norm)
         c.no_feat_proj_ln = int(not cfg.feat_proj_layer_norm)
+        c.vocab_size, c.max_positions = cfg.vocab_size, cfg.max_position_embeddings
+        c.type_vocab_size, c.pad_token_id = cfg.type_vocab_size, cfg.pad_token_id
         if cfg.arch == ARCH_W2V:
             if cfg.feat_extract_norm not in ("layer", "group"):
                 raise ValueError(f"feat_extract_norm={cfg.feat_extract_norm!r} has to be 'layer' or 'group'")
@@ -168,9 +184,23 @@ class Engine:
             self.close()
             raise
         self._tls = threading.local()
+        self._graphs: "OrderedDict[tuple, tuple]" = OrderedDict()   # CUDA-graph cache of small encode calls (encode_w2v_graphed)
+        self._graph_lock = threading.Lock()
 
     # ------------------------------------------------------------------ lifecycle
+    def synchronize(self) -> None:
+        """Wait for the current stream and surface an asynchronous kernel fault as SerencError (the handle is then
+        poisoned: every later call fails with the same message, include/serenc.h)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_sync(self._h, _stream_ptr(self.device)))
+
+    @property
+    def poisoned(self) -> bool:
+        return bool(self._h) and bool(self._lib.serenc_is_poisoned(self._h))
+
     def close(self) -> None:
+        if getattr(self, "_graphs", None):
+            self._graphs.clear()
         if getattr(self, "_h", None):
             self._lib.serenc_destroy(self._h)
             self._h = None
@@ -224,34 +254,106 @@ class Engine:
 
     def encode_w2v(self, wav: torch.Tensor, starts: Sequence[int], lens: Sequence[int], *, normalize: bool,
                    layers: Iterable[int], reduce: int = REDUCE_NONE, want_frames: bool = True,
-                   want_pooled: bool = False):
-        """Returns (frames | None, pooled | None, frame_offsets[B+1], selected layer indices).
-        frames: [n_sel, sum_T, d] (REDUCE_NONE) or [sum_T, d]; pooled: [n_sel, B, d] or [B, d]."""
-        assert wav.is_cuda and wav.dtype == torch.float32 and wav.is_contiguous()
+                   want_pooled: bool = False, layer_weights: Optional[Sequence[float]] = None,
+                   want_extract_features: bool = False):
+        """Returns (frames | None, pooled | None, frame_offsets[B+1], selected layer indices[, extract_features]).
+        frames: [n_sel, sum_T, d] (REDUCE_NONE) or [sum_T, d]; pooled: [n_sel, B, d] or [B, d].
+        wav: float32 samples or int16 PCM (scaled by 1/32768 inside the kernels, as librosa does on the host).
+        layer_weights: one weight per selected layer (ascending index) for REDUCE_WEIGHTED.
+        want_extract_features: additionally return HF's `extract_features` [sum_T, conv_dim] fp32 as a fifth value."""
+        assert wav.is_cuda and wav.is_contiguous()
+        wav_dtype = _wav_dtype(wav)
         B = len(lens)
         mask, idx = layer_mask_of(layers, self.cfg.num_hidden_layers)
+        if reduce == REDUCE_WEIGHTED and (layer_weights is None or len(layer_weights) != len(idx)):
+            raise ValueError(f"REDUCE_WEIGHTED needs one weight per selected layer ({len(idx)})")
         T = [w2v_num_frames(n, self.cfg) for n in lens]
         for b, t in enumerate(T):
             if t < 1:
                 raise ValueError(f"utterance {b}: {lens[b]} samples is shorter than the 400-sample receptive field")
         sumT, d = sum(T), self.cfg.hidden_size
-        lead = () if reduce == REDUCE_MEAN else (len(idx),)
+        lead = () if reduce != REDUCE_NONE else (len(idx),)
         frames = torch.empty(lead + (sumT, d), dtype=torch.float32, device=self.device) if want_frames else None
         pooled = torch.empty(lead + (B, d), dtype=torch.float32, device=self.device) if want_pooled else None
+        feats = torch.empty((sumT, self.cfg.conv_dim[-1]), dtype=torch.float32, device=self.device) if want_extract_features else None
         ws = self._workspace(self.w2v_workspace_bytes(lens))
         offs = (C.c_int64 * (B + 1))()
+        call = _lib.SerencW2VCall()
+        call.wav_dev, call.wav_dtype, call.batch = wav.data_ptr(), wav_dtype, B
+        call.sample_start, call.sample_len = _lib.i64_array(starts), _lib.i32_array(lens)
+        call.normalize, call.reduce, call.layer_mask = int(normalize), reduce, mask
+        if reduce == REDUCE_WEIGHTED:
+            call.layer_weights = _lib.f32_array(layer_weights)
+        call.frames_out_dev, call.pooled_out_dev, call.extract_features_out_dev = _ptr(frames), _ptr(pooled), _ptr(feats)
+        call.frame_offsets_out = offs
+        call.workspace_dev, call.workspace_bytes = ws.data_ptr(), ws.numel()
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.serenc_encode_w2v(
-                self._h, wav.data_ptr(), _lib.i64_array(starts), _lib.i32_array(lens), B, int(normalize), mask, reduce,
-                _ptr(frames), _ptr(pooled), offs, ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+            call.stream = _stream_ptr(self.device)
+            _lib.check(self._lib.serenc_encode_w2v_ex(self._h, C.byref(call)))
+        if want_extract_features:
+            return frames, pooled, list(offs), idx, feats
         return frames, pooled, list(offs), idx
 
+    # Small batches are launch-bound (~250 launches of a few microseconds: 8 x 4 s takes 3.3 ms eager, 2.9 ms replayed,
+    # profiles/r01_notes.md), so pooled-only calls below this many frames are captured into a CUDA graph once per length
+    # signature and replayed; larger batches are not launch-bound and stay eager.
+    GRAPH_MAX_FRAMES = 4096
+    GRAPH_CACHE_SIZE = 16
+
+    def encode_w2v_graphed(self, wav: torch.Tensor, starts: Sequence[int], lens: Sequence[int], *, normalize: bool,
+                           layers: Iterable[int], reduce: int, layer_weights: Optional[Sequence[float]] = None):
+        """Pooled-only encode_w2v through a CUDA graph keyed on (lengths, layers, reduce, weights, dtype). The waveform is
+        copied into the graph's static input buffer and the pooled result is cloned out of its static output, so the
+        call is interchangeable with the eager one (bit-identical results: the same kernels in the same order)."""
+        # the stream is part of the key: every stream replays its own graph with its own static buffers
+        key = (tuple(int(n) for n in lens), tuple(int(v) for v in starts), tuple(sorted(layers)), int(reduce),
+               None if layer_weights is None else tuple(float(v) for v in layer_weights), wav.dtype, bool(normalize),
+               _stream_ptr(self.device))
+        with self._graph_lock:
+            ent = self._graphs.get(key)
+            if ent is not None:
+                self._graphs.move_to_end(key)
+        if ent is None:
+            static_in = torch.empty_like(wav)
+            static_in.copy_(wav)
+            # capture on a side stream with a workspace that belongs to the graph
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            saved_ws = getattr(self._tls, "ws", None)
+            self._tls.ws = None
+            try:
+                with torch.cuda.stream(side):
+                    self.encode_w2v(static_in, starts, lens, normalize=normalize, layers=layers, reduce=reduce, want_frames=False,
+                                    want_pooled=True, layer_weights=layer_weights)   # warm-up: allocates the workspace
+                    side.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        _, pooled, offs, idx = self.encode_w2v(static_in, starts, lens, normalize=normalize, layers=layers, reduce=reduce,
+                                                               want_frames=False, want_pooled=True, layer_weights=layer_weights)
+                graph_ws = self._tls.ws
+            finally:
+                self._tls.ws = saved_ws
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            ent = (graph, static_in, pooled, offs, idx, graph_ws)
+            with self._graph_lock:
+                self._graphs[key] = ent
+                while len(self._graphs) > self.GRAPH_CACHE_SIZE:
+                    self._graphs.popitem(last=False)
+        graph, static_in, pooled, offs, idx, _ = ent
+        with self._graph_lock:   # threads that share a stream: copy-in / replay / copy-out enqueued as one unit
+            static_in.copy_(wav, non_blocking=True)
+            graph.replay()
+            out = pooled.clone()
+        return None, out, list(offs), idx
+
     def unpack(self, packed: torch.Tensor, offsets: Sequence[int], t_max: int) -> torch.Tensor:
+        """packed [sum_T, cols] -> HF-shaped [B, t_max, cols] (pad frames zero)."""
         B = len(offsets) - 1
-        out = torch.empty((B, t_max, self.cfg.hidden_size), dtype=torch.float32, device=self.device)
+        cols = int(packed.shape[-1])
+        out = torch.empty((B, t_max, cols), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.serenc_unpack_frames(self._h, packed.data_ptr(), _lib.i64_array(offsets), B, t_max,
-                                                      out.data_ptr(), _stream_ptr(self.device)))
+            _lib.check(self._lib.serenc_unpack_rows(self._h, packed.data_ptr(), _lib.i64_array(offsets), B, t_max, cols,
+                                                    out.data_ptr(), _stream_ptr(self.device)))
         return out
 
     # ------------------------------------------------------------------ whisper
@@ -260,8 +362,8 @@ class Engine:
         mel = torch.empty((B, self.cfg.num_mel_bins, 3000), dtype=torch.float32, device=self.device)
         scratch = torch.empty(64 + 40 * B + 64, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.serenc_logmel(self._h, wav.data_ptr(), _lib.i64_array(starts), _lib.i32_array(lens), B,
-                                               mel.data_ptr(), scratch.data_ptr(), _stream_ptr(self.device)))
+            _lib.check(self._lib.serenc_logmel_ex(self._h, wav.data_ptr(), _wav_dtype(wav), _lib.i64_array(starts), _lib.i32_array(lens), B,
+                                                  mel.data_ptr(), scratch.data_ptr(), _stream_ptr(self.device)))
         return mel
 
     def whisper_workspace_bytes(self, batch: int) -> int:
@@ -270,7 +372,8 @@ class Engine:
         return int(out.value)
 
     def encode_whisper(self, mel: torch.Tensor, *, layers: Iterable[int], reduce: int = REDUCE_NONE,
-                       n_keep: Optional[Sequence[int]] = None, want_frames: bool = True, want_pooled: bool = False):
+                       n_keep: Optional[Sequence[int]] = None, want_frames: bool = True, want_pooled: bool = False,
+                       layer_weights: Optional[Sequence[float]] = None):
         assert mel.is_cuda and mel.dtype == torch.float32 and mel.is_contiguous()
         if mel.dim() != 3 or mel.shape[1] != self.cfg.num_mel_bins or mel.shape[2] != 3000:
             # HF WhisperEncoder.forward raises ValueError here (modeling_whisper.py:613-617)
@@ -279,12 +382,41 @@ class Engine:
         B = mel.shape[0]
         mask, idx = layer_mask_of(layers, self.cfg.num_hidden_layers)
         d = self.cfg.hidden_size
-        lead = () if reduce == REDUCE_MEAN else (len(idx),)
+        if reduce == REDUCE_WEIGHTED and (layer_weights is None or len(layer_weights) != len(idx)):
+            raise ValueError(f"REDUCE_WEIGHTED needs one weight per selected layer ({len(idx)})")
+        lead = () if reduce != REDUCE_NONE else (len(idx),)
         frames = torch.empty(lead + (B * 1500, d), dtype=torch.float32, device=self.device) if want_frames else None
         pooled = torch.empty(lead + (B, d), dtype=torch.float32, device=self.device) if want_pooled else None
         ws = self._workspace(self.whisper_workspace_bytes(B))
         keep = _lib.i32_array(n_keep) if n_keep is not None else None
+        lw = _lib.f32_array(layer_weights) if reduce == REDUCE_WEIGHTED else None
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.serenc_encode_whisper(self._h, mel.data_ptr(), B, mask, reduce, keep, _ptr(frames),
-                                                       _ptr(pooled), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+            _lib.check(self._lib.serenc_encode_whisper_ex(self._h, mel.data_ptr(), B, mask, reduce, lw, keep, _ptr(frames),
+                                                          _ptr(pooled), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
+        return frames, pooled, idx
+
+    # ------------------------------------------------------------------ text encoder
+    def text_workspace_bytes(self, batch: int, seq_len: int) -> int:
+        out = C.c_size_t()
+        _lib.check(self._lib.serenc_text_workspace_bytes(self._h, batch, seq_len, C.byref(out)))
+        return int(out.value)
+
+    def encode_text(self, input_ids: torch.Tensor, valid_len: Sequence[int], *, layers: Iterable[int], reduce: int = REDUCE_NONE,
+                    want_frames: bool = True, want_pooled: bool = False, layer_weights: Optional[Sequence[float]] = None):
+        """input_ids: [B, T] int32 on the device, right-padded; valid_len[b] = non-pad tokens of row b.
+        Returns (frames [n_sel, B*T, d] | [B*T, d] | None, pooled | None, selected layer indices)."""
+        assert input_ids.is_cuda and input_ids.dtype == torch.int32 and input_ids.is_contiguous() and input_ids.dim() == 2
+        B, T = input_ids.shape
+        mask, idx = layer_mask_of(layers, self.cfg.num_hidden_layers)
+        if reduce == REDUCE_WEIGHTED and (layer_weights is None or len(layer_weights) != len(idx)):
+            raise ValueError(f"REDUCE_WEIGHTED needs one weight per selected layer ({len(idx)})")
+        d = self.cfg.hidden_size
+        lead = () if reduce != REDUCE_NONE else (len(idx),)
+        frames = torch.empty(lead + (B * T, d), dtype=torch.float32, device=self.device) if want_frames else None
+        pooled = torch.empty(lead + (B, d), dtype=torch.float32, device=self.device) if want_pooled else None
+        ws = self._workspace(self.text_workspace_bytes(B, T))
+        lw = _lib.f32_array(layer_weights) if reduce == REDUCE_WEIGHTED else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.serenc_encode_text(self._h, input_ids.data_ptr(), _lib.i32_array(valid_len), B, T, mask, reduce, lw,
+                                                    _ptr(frames), _ptr(pooled), ws.data_ptr(), ws.numel(), _stream_ptr(self.device)))
         return frames, pooled, idx

@@ -22,8 +22,8 @@ import numpy as np
 import torch
 
 from . import weights as W
-from .configs import ARCH_WHISPER, EncoderConfig, get_config, w2v_num_frames
-from .engine import REDUCE_MEAN, REDUCE_NONE, Engine, UploadRing
+from .configs import ARCH_TEXT, ARCH_WHISPER, EncoderConfig, get_config, w2v_num_frames
+from .engine import REDUCE_MEAN, REDUCE_NONE, REDUCE_WEIGHTED, Engine, UploadRing
 from .feature_extraction import Wav2Vec2FeatureExtractor, WhisperFeatureExtractor, WhisperProcessor
 
 
@@ -79,6 +79,16 @@ class Extracted:
     num_frames: List[int]
     packed: Optional[torch.Tensor] = None  # the [rows, d] device tensor `frames` are views of (one D2H moves them all)
     ranges: Optional[List[Tuple[int, int]]] = None   # row range of every utterance inside `packed`
+
+
+def _pack_host(waveforms: Sequence[np.ndarray]) -> torch.Tensor:
+    """Utterances back to back in one pinned host tensor: int16 when every input is int16 PCM, else float32."""
+    if len(waveforms) and all(getattr(w, "dtype", None) == np.int16 for w in waveforms):
+        flat = np.concatenate([np.asarray(w, dtype=np.int16) for w in waveforms])
+    else:
+        flat = np.concatenate([np.asarray(w, dtype=np.float32) if getattr(w, "dtype", None) != np.int16
+                               else np.asarray(w, dtype=np.float32) / np.float32(32768.0) for w in waveforms])
+    return torch.from_numpy(flat).pin_memory()
 
 
 class _Base:
@@ -137,11 +147,104 @@ class _Base:
     def freeze_feature_encoder(self):
         return None
 
-    def _select(self, layer: int, average: bool) -> Tuple[List[int], int]:
+    def _select(self, layer: int, average: bool, layer_weights: Optional[Sequence[float]] = None,
+                layers: Optional[Sequence[int]] = None) -> Tuple[List[int], int, Optional[List[float]]]:
+        """-> (hidden-state indices, reduce mode, per-layer weights in ascending layer order)."""
+        n = self.cfg.num_hidden_layers + 1
+        if layer_weights is not None:
+            # softmax-weighted layer sum (lora_wavlm/model.py:164-181): weights for `layers` (default: all but the conv
+            # output, the reference's use_conv_output = False); the caller has applied the softmax
+            sel = list(layers) if layers is not None else list(range(n - len(layer_weights), n))
+            sel = [(i + n) if i < 0 else i for i in sel]
+            if len(sel) != len(layer_weights) or len(set(sel)) != len(sel):
+                raise ValueError("layer_weights needs one weight per distinct selected layer")
+            order = sorted(range(len(sel)), key=lambda j: sel[j])
+            return [sel[j] for j in order], REDUCE_WEIGHTED, [float(layer_weights[j]) for j in order]
         if average:  # torch.stack(hidden_states[-4:]) — Python slicing: fewer than 4 states means "all of them"
-            n = self.cfg.num_hidden_layers + 1
-            return list(range(max(0, n - 4), n)), REDUCE_MEAN
-        return [layer], REDUCE_NONE
+            return list(range(max(0, n - 4), n)), REDUCE_MEAN, None
+        return [layer], REDUCE_NONE, None
+
+    # ---- request coalescing for the reference's unchanged 4-thread call pattern (preprocess_speech.py:120-122) ----
+    def enable_request_batching(self, max_batch: int = 64, max_wait_ms: float = 2.0) -> "_Base":
+        """Concurrent `model(**inputs)` calls (one utterance each, as the reference's ThreadPoolExecutor issues them) are
+        collected by a dispatcher thread and encoded as ONE packed batch; every caller gets exactly the result the
+        batch-1 call would have produced (batching invariance is bit-exact, tests/test_gpu_models.py)."""
+        if getattr(self, "_queue", None) is None:
+            self._queue = _CoalescingQueue(self, max_batch, max_wait_ms)
+        return self
+
+    def disable_request_batching(self) -> None:
+        q = getattr(self, "_queue", None)
+        if q is not None:
+            q.close()
+            self._queue = None
+
+
+class _CoalescingQueue:
+    """Dispatcher thread behind enable_request_batching(). A request is (run, args): `collect` turns the requests that
+    are pending at the same time into one engine call and hands every caller its slice."""
+
+    def __init__(self, model: "_Base", max_batch: int, max_wait_ms: float):
+        import queue
+
+        self.model = model
+        self.max_batch = max(1, int(max_batch))
+        self.max_wait = max(0.0, float(max_wait_ms)) / 1e3
+        self.q: "queue.Queue" = queue.Queue()
+        self.batches = 0          # statistics: engine calls issued / requests served
+        self.requests = 0
+        self._closed = False
+        self._thread = threading.Thread(target=self._loop, name="serenc-batcher", daemon=True)
+        self._thread.start()
+
+    def submit(self, item):
+        from concurrent.futures import Future
+
+        if self._closed:
+            raise RuntimeError("request batching was disabled")
+        fut: Future = Future()
+        self.q.put((item, fut))
+        return fut
+
+    def close(self):
+        self._closed = True
+        self.q.put(None)
+        self._thread.join(timeout=5.0)
+
+    def _loop(self):
+        import queue
+        import time
+
+        while True:
+            first = self.q.get()
+            if first is None:
+                return
+            group = [first]
+            deadline = time.monotonic() + self.max_wait
+            while len(group) < self.max_batch:
+                try:
+                    nxt = self.q.get(timeout=max(0.0, deadline - time.monotonic()))
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self.q.put(None)
+                    break
+                group.append(nxt)
+            # requests that ask for different outputs cannot share a call
+            by_kind: Dict[object, list] = {}
+            for item, fut in group:
+                by_kind.setdefault(item[0], []).append((item, fut))
+            for kind, members in by_kind.items():
+                try:
+                    results = self.model._run_coalesced(kind, [it for it, _ in members])
+                    self.batches += 1
+                    self.requests += len(members)
+                    for (_, fut), res in zip(members, results):
+                        fut.set_result(res)
+                except BaseException as e:  # noqa: BLE001 - every waiting caller must be released
+                    for _, fut in members:
+                        if not fut.done():
+                            fut.set_exception(e)
 
 
 class SpeechEncoderModel(_Base):
@@ -154,49 +257,115 @@ class SpeechEncoderModel(_Base):
             raise NotImplementedError("attention probabilities are never materialised by the flash-style kernel")
         if input_values.dim() == 1:
             input_values = input_values[None]
-        x = input_values.to(self.device, torch.float32).contiguous()
-        B, Lmax = x.shape
+        B, Lmax = input_values.shape
         if attention_mask is not None:
             lens = [int(v) for v in attention_mask.to(torch.float32).ne(0).sum(-1).tolist()]
         else:
             lens = [Lmax] * B
-        starts = [b * Lmax for b in range(B)]
-        L = self.cfg.num_hidden_layers
-        layers = range(L + 1) if output_hidden_states else [L]
-        frames, _, offs, idx = self.engine.encode_w2v(x, starts, lens, normalize=False, layers=layers,
-                                                      reduce=REDUCE_NONE, want_frames=True, want_pooled=False)
-        t_max = w2v_num_frames(Lmax, self.cfg)
-        if B == 1:
-            hs = tuple(frames[i].view(1, t_max, -1) for i in range(len(idx)))
-        else:
-            hs = tuple(self.engine.unpack(frames[i], offs, t_max) for i in range(len(idx)))
-        return ModelOutput(last_hidden_state=hs[-1], extract_features=None, hidden_states=hs if output_hidden_states else None)
+        q = getattr(self, "_queue", None)
+        if q is not None and threading.current_thread() is not q._thread:
+            # one utterance per call from several threads: coalesced into one packed batch by the dispatcher
+            item = (bool(output_hidden_states), input_values, lens)
+            return q.submit(item).result()
+        return self._forward_batch(input_values, lens, bool(output_hidden_states))
 
     __call__ = forward
 
-    @torch.no_grad()
-    def extract(self, waveforms: Sequence[np.ndarray], layer: int = -1, average: bool = False, want_frames: bool = True,
-                want_pooled: bool = True) -> Extracted:
-        """Batched embedding extraction: raw 16 kHz waveforms -> hidden_states[layer] (or mean of the last four,
-        preprocess_speech.py:56-63) per utterance + masked-mean pooled vectors. One H2D copy, one encode call."""
-        lens = [int(len(w)) for w in waveforms]
-        flat = torch.from_numpy(np.concatenate([np.asarray(w, dtype=np.float32) for w in waveforms]))
-        return self.extract_pinned(flat.pin_memory(), lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled)
+    def _forward_batch(self, input_values: torch.Tensor, lens: Sequence[int], all_states: bool) -> ModelOutput:
+        x = input_values.to(self.device, torch.float32).contiguous()
+        B, Lmax = x.shape
+        starts = [b * Lmax for b in range(B)]
+        L = self.cfg.num_hidden_layers
+        layers = range(L + 1) if all_states else [L]
+        want_feats = self.cfg.feat_proj_layer_norm and self.cfg.family != "hubert"   # HubertModel returns no extract_features
+        res = self.engine.encode_w2v(x, starts, lens, normalize=False, layers=layers, reduce=REDUCE_NONE, want_frames=True,
+                                     want_pooled=False, want_extract_features=want_feats)
+        frames, _, offs, idx = res[:4]
+        t_max = w2v_num_frames(Lmax, self.cfg)
+        if B == 1 and offs[1] == t_max:     # a single full-length row: the packed matrix IS the padded one
+            unpack = lambda t: t.view(1, t_max, -1)  # noqa: E731
+        else:
+            unpack = lambda t: self.engine.unpack(t, offs, t_max)  # noqa: E731
+        hs = tuple(unpack(frames[i]) for i in range(len(idx)))
+        feats = unpack(res[4]) if want_feats else None
+        return ModelOutput(last_hidden_state=hs[-1], extract_features=feats, hidden_states=hs if all_states else None)
 
-    @torch.no_grad()
-    def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
-                       want_frames: bool = False, want_pooled: bool = True) -> Extracted:
-        """Same as extract() for a packed waveform tensor already resident on the device."""
+    def _run_coalesced(self, all_states: bool, items) -> List[ModelOutput]:
+        """Requests collected by the dispatcher -> one packed encode -> one HF-shaped output per request."""
+        rows, lens, owner = [], [], []
+        for ri, (_, iv, ls) in enumerate(items):
+            iv = iv.to(self.device, torch.float32)
+            for b, n in enumerate(ls):
+                rows.append(iv[b, :n])
+                lens.append(n)
+                owner.append(ri)
+        flat = torch.cat(rows).contiguous()
         starts, off = [], 0
         for n in lens:
             starts.append(off)
             off += n
-        layers, reduce = self._select(layer, average)
-        frames, pooled, offs, _ = self.engine.encode_w2v(wav, starts, lens, normalize=self.cfg.do_normalize, layers=layers,
-                                                         reduce=reduce, want_frames=want_frames, want_pooled=want_pooled)
+        L = self.cfg.num_hidden_layers
+        layers = range(L + 1) if all_states else [L]
+        want_feats = self.cfg.feat_proj_layer_norm and self.cfg.family != "hubert"
+        res = self.engine.encode_w2v(flat, starts, lens, normalize=False, layers=layers, reduce=REDUCE_NONE, want_frames=True,
+                                     want_pooled=False, want_extract_features=want_feats)
+        frames, _, offs, idx = res[:4]
+        outs: List[ModelOutput] = []
+        u = 0
+        for ri, (_, iv, ls) in enumerate(items):
+            B, Lmax = iv.shape
+            t_max = w2v_num_frames(Lmax, self.cfg)
+            sub = [o - offs[u] for o in offs[u:u + B + 1]]
+            a, e = offs[u], offs[u + B]
+
+            def unpack(t, a=a, e=e, sub=sub, B=B, t_max=t_max):
+                if B == 1 and sub[1] == t_max:
+                    return t[a:e].view(1, t_max, -1)
+                return self.engine.unpack(t[a:e].contiguous(), sub, t_max)
+            hs = tuple(unpack(frames[i]) for i in range(len(idx)))
+            outs.append(ModelOutput(last_hidden_state=hs[-1], extract_features=unpack(res[4]) if want_feats else None,
+                                    hidden_states=hs if all_states else None))
+            u += B
+        return outs
+
+    @torch.no_grad()
+    def extract(self, waveforms: Sequence[np.ndarray], layer: int = -1, average: bool = False, want_frames: bool = True,
+                want_pooled: bool = True, **kw) -> Extracted:
+        """Batched embedding extraction: raw 16 kHz waveforms -> hidden_states[layer] (or mean of the last four,
+        preprocess_speech.py:56-63) per utterance + masked-mean pooled vectors. One H2D copy, one encode call.
+        Waveforms may be float32 samples or int16 PCM (all of one kind): int16 halves the upload and is scaled by
+        1 / 32768 inside the first kernel, exactly as librosa scales it on the host."""
+        lens = [int(len(w)) for w in waveforms]
+        return self.extract_pinned(_pack_host(waveforms), lens, layer=layer, average=average, want_frames=want_frames,
+                                   want_pooled=want_pooled, **kw)
+
+    @torch.no_grad()
+    def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
+                       want_frames: bool = False, want_pooled: bool = True, layer_weights: Optional[Sequence[float]] = None,
+                       layers: Optional[Sequence[int]] = None, use_graph: Optional[bool] = None) -> Extracted:
+        """Same as extract() for a packed waveform tensor already resident on the device.
+        layer_weights (+ optional layers): weighted sum of hidden states instead of one layer / the mean of the last four.
+        use_graph: replay small pooled-only calls from a CUDA graph cached per length signature (default: automatic)."""
+        starts, off = [], 0
+        for n in lens:
+            starts.append(off)
+            off += n
+        sel, reduce, lw = self._select(layer, average, layer_weights, layers)
+        graph_ok = (want_pooled and not want_frames and reduce != REDUCE_NONE
+                    and sum(w2v_num_frames(n, self.cfg) for n in lens) <= self.engine.GRAPH_MAX_FRAMES
+                    and not torch.cuda.is_current_stream_capturing())
+        if use_graph is None:
+            use_graph = graph_ok and os.environ.get("SERENC_NO_GRAPH") != "1"
+        if use_graph and graph_ok:
+            frames, pooled, offs, _ = self.engine.encode_w2v_graphed(wav, starts, lens, normalize=self.cfg.do_normalize, layers=sel,
+                                                                     reduce=reduce, layer_weights=lw)
+        else:
+            frames, pooled, offs, _ = self.engine.encode_w2v(wav, starts, lens, normalize=self.cfg.do_normalize, layers=sel,
+                                                             reduce=reduce, want_frames=want_frames, want_pooled=want_pooled,
+                                                             layer_weights=lw)
         per_utt, f2, ranges = None, None, None
         if frames is not None:
-            f2 = frames if reduce == REDUCE_MEAN else frames[0]
+            f2 = frames if reduce != REDUCE_NONE else frames[0]
             ranges = [(offs[b], offs[b + 1]) for b in range(len(lens))]
             per_utt = [f2[a:e] for a, e in ranges]
         if pooled is not None and reduce == REDUCE_NONE:
@@ -239,19 +408,19 @@ class WhisperModel(_Base):
 
     @torch.no_grad()
     def extract(self, waveforms: Sequence[np.ndarray], layer: int = -1, average: bool = False, want_frames: bool = True,
-                want_pooled: bool = True, literal_crop: bool = True) -> Extracted:
+                want_pooled: bool = True, literal_crop: bool = True, **kw) -> Extracted:
         """log-mel -> encoder -> hidden_states[layer] | mean of last four -> keep the first
         min(ceil(len/320), cap) frames (preprocess_whisper.py:49-50,75-76; cap = hidden size when literal_crop,
-        reproducing the script's `feats.shape[1]`, else 1500)."""
-        waveforms = [np.asarray(w, dtype=np.float32)[:480000] for w in waveforms]
+        reproducing the script's `feats.shape[1]`, else 1500). float32 samples or int16 PCM."""
+        waveforms = [np.asarray(w)[:480000] for w in waveforms]
         lens = [int(len(w)) for w in waveforms]
-        flat = torch.from_numpy(np.concatenate(waveforms)).pin_memory()
-        return self.extract_pinned(flat, lens, layer=layer, average=average, want_frames=want_frames, want_pooled=want_pooled,
-                                   literal_crop=literal_crop)
+        return self.extract_pinned(_pack_host(waveforms), lens, layer=layer, average=average, want_frames=want_frames,
+                                   want_pooled=want_pooled, literal_crop=literal_crop, **kw)
 
     @torch.no_grad()
     def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
-                       want_frames: bool = False, want_pooled: bool = True, literal_crop: bool = True) -> Extracted:
+                       want_frames: bool = False, want_pooled: bool = True, literal_crop: bool = True,
+                       layer_weights: Optional[Sequence[float]] = None, layers: Optional[Sequence[int]] = None) -> Extracted:
         starts, off = [], 0
         for n in lens:
             starts.append(off)
@@ -259,12 +428,12 @@ class WhisperModel(_Base):
         mel = self.engine.logmel(wav, starts, lens)
         cap = self.cfg.hidden_size if literal_crop else 1500
         keep = [max(1, min(-(-n // 320), cap, 1500)) for n in lens]
-        layers, reduce = self._select(layer, average)
-        frames, pooled, _ = self.engine.encode_whisper(mel, layers=layers, reduce=reduce, n_keep=keep, want_frames=want_frames,
-                                                       want_pooled=want_pooled)
+        sel, reduce, lw = self._select(layer, average, layer_weights, layers)
+        frames, pooled, _ = self.engine.encode_whisper(mel, layers=sel, reduce=reduce, n_keep=keep, want_frames=want_frames,
+                                                       want_pooled=want_pooled, layer_weights=lw)
         per_utt, f2, ranges = None, None, None
         if frames is not None:
-            f2 = frames if reduce == REDUCE_MEAN else frames[0]
+            f2 = frames if reduce != REDUCE_NONE else frames[0]
             ranges = [(b * 1500, b * 1500 + keep[b]) for b in range(len(lens))]
             per_utt = [f2[a:e] for a, e in ranges]
         if pooled is not None and reduce == REDUCE_NONE:
@@ -304,7 +473,13 @@ class AutoModel:
         tensors = _resolve_weights(cfg, name_or_path, random_init, seed)
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() else 0
-        model = (WhisperModel if cfg.arch == ARCH_WHISPER else SpeechEncoderModel)(cfg, tensors, device)
+        if cfg.arch == ARCH_TEXT:
+            from .text import RobertaModel
+            model = RobertaModel(cfg, tensors, device)
+        else:
+            model = (WhisperModel if cfg.arch == ARCH_WHISPER else SpeechEncoderModel)(cfg, tensors, device)
+        if os.environ.get("SERENC_BATCH_REQUESTS") == "1" and cfg.arch not in (ARCH_TEXT, ARCH_WHISPER):
+            model.enable_request_batching()
         _LAST_MODEL[cfg.name] = model
         return model
 

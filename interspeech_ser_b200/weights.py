@@ -12,6 +12,9 @@ Canonical names (the table INTEGRATION.md documents; consumed by serenc_load_ten
   layer{i}.gru.weight|bias|const (WavLM)
   final_ln.weight|bias                                       (both)
 
+  RoBERTa (text branch): embed.word, embed.position, embed.type, final_ln.* (= embeddings.LayerNorm, the stack's
+  leading LayerNorm), layer{i}.* as above with ln1 = attention.output.LayerNorm, ln2 = output.LayerNorm.
+
 All tensors are fp32 numpy arrays on the host; dtype/layout conversion for the tensor cores happens inside
 the library at load time.
 """
@@ -24,7 +27,7 @@ from typing import Dict, Mapping
 
 import numpy as np
 
-from .configs import ARCH_WHISPER, EncoderConfig
+from .configs import ARCH_TEXT, ARCH_WHISPER, EncoderConfig
 
 
 def _np(t) -> np.ndarray:
@@ -129,12 +132,28 @@ def from_hf_state_dict(cfg: EncoderConfig, sd: Mapping[str, object], lora_alpha:
     sd = dict(sd)
     if any(".lora_A." in k for k in sd):
         sd = merge_lora(sd, lora_alpha)
-    # strip wrapper prefixes: "wavlm.", "wav2vec2.", "hubert.", "model."
-    for prefix in ("wavlm.", "wav2vec2.", "hubert.", "model."):
+    # strip wrapper prefixes: "wavlm.", "wav2vec2.", "hubert.", "model." (and peft's "whisper." / "roberta." task wrappers)
+    for prefix in ("wavlm.", "wav2vec2.", "hubert.", "whisper.", "roberta.", "model."):
         if any(k.startswith(prefix) for k in sd):
             sd = {(k[len(prefix):] if k.startswith(prefix) else k): v for k, v in sd.items()}
     out: Dict[str, np.ndarray] = {}
     L = cfg.num_hidden_layers
+    if cfg.arch == ARCH_TEXT:
+        # RobertaModel (HF modeling_roberta.py): RobertaEmbeddings + RobertaLayer x L; the pooler is not on this path
+        e = "embeddings."
+        out["embed.word"] = _np(sd[e + "word_embeddings.weight"])
+        out["embed.position"] = _np(sd[e + "position_embeddings.weight"])
+        out["embed.type"] = _np(sd[e + "token_type_embeddings.weight"])
+        out["final_ln.weight"] = _np(sd[e + "LayerNorm.weight"])
+        out["final_ln.bias"] = _np(sd[e + "LayerNorm.bias"])
+        for i in range(L):
+            b = f"encoder.layer.{i}."
+            for s_, t_ in (("q", "attention.self.query"), ("k", "attention.self.key"), ("v", "attention.self.value"),
+                           ("o", "attention.output.dense"), ("fc1", "intermediate.dense"), ("fc2", "output.dense"),
+                           ("ln1", "attention.output.LayerNorm"), ("ln2", "output.LayerNorm")):
+                out[f"layer{i}.{s_}.weight"] = _np(sd[b + t_ + ".weight"])
+                out[f"layer{i}.{s_}.bias"] = _np(sd[b + t_ + ".bias"])
+        return out
     if cfg.arch == ARCH_WHISPER:
         pre = "encoder." if any(k.startswith("encoder.") for k in sd) else ""
         out["conv1.weight"] = _np(sd[pre + "conv1.weight"])
@@ -238,6 +257,13 @@ def random_init(cfg: EncoderConfig, seed: int = 0) -> Dict[str, np.ndarray]:
             out[f"layer{i}.gru.bias"] = normal((8,), 0.1)
             out[f"layer{i}.gru.const"] = (1.0 + 0.1 * rng.standard_normal(H, dtype=np.float32)).astype(np.float32)
     out["final_ln.weight"], out["final_ln.bias"] = ln(d)
+    if cfg.arch == ARCH_TEXT:
+        out["embed.word"] = normal((cfg.vocab_size, d), 0.5)
+        out["embed.position"] = normal((cfg.max_position_embeddings, d), 0.5)
+        out["embed.type"] = normal((cfg.type_vocab_size, d), 0.5)
+        for k in ("word", "position"):   # nn.Embedding(padding_idx=pad): that row is zero in HF checkpoints
+            out[f"embed.{k}"][cfg.pad_token_id] = 0.0
+        return out
     if cfg.arch == ARCH_WHISPER:
         nm = cfg.num_mel_bins
         out["conv1.weight"] = normal((d, nm, 3), math.sqrt(2.0 / (nm * 3)))

@@ -123,6 +123,76 @@ def hf_model(cfg: C.EncoderConfig, w):
     return m
 
 
+def hf_roberta(cfg: C.EncoderConfig, w):
+    """canonical text-encoder weights -> HF RobertaModel (no pooler: it is not on this path)."""
+    import transformers as tr
+
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))  # noqa: E731
+    hc = tr.RobertaConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_hidden_layers,
+                          num_attention_heads=cfg.num_attention_heads, intermediate_size=cfg.intermediate_size,
+                          hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                          max_position_embeddings=cfg.max_position_embeddings, type_vocab_size=cfg.type_vocab_size,
+                          layer_norm_eps=cfg.layer_norm_eps, pad_token_id=cfg.pad_token_id, bos_token_id=0, eos_token_id=2)
+    m = tr.RobertaModel(hc, add_pooling_layer=False).eval()
+    sd = {"embeddings.word_embeddings.weight": t(w["embed.word"]), "embeddings.position_embeddings.weight": t(w["embed.position"]),
+          "embeddings.token_type_embeddings.weight": t(w["embed.type"]),
+          "embeddings.LayerNorm.weight": t(w["final_ln.weight"]), "embeddings.LayerNorm.bias": t(w["final_ln.bias"])}
+    names = (("q", "attention.self.query"), ("k", "attention.self.key"), ("v", "attention.self.value"),
+             ("o", "attention.output.dense"), ("fc1", "intermediate.dense"), ("fc2", "output.dense"),
+             ("ln1", "attention.output.LayerNorm"), ("ln2", "output.LayerNorm"))
+    for i in range(cfg.num_hidden_layers):
+        for s_, t_ in names:
+            sd[f"encoder.layer.{i}.{t_}.weight"] = t(w[f"layer{i}.{s_}.weight"])
+            sd[f"encoder.layer.{i}.{t_}.bias"] = t(w[f"layer{i}.{s_}.bias"])
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(("position_ids" in k or "token_type_ids" in k) for k in missing), missing
+    # round trip of the product's own converter on the HF state dict
+    from interspeech_ser_b200.weights import from_hf_state_dict
+    back = from_hf_state_dict(cfg, m.state_dict())
+    for k, v in w.items():
+        assert np.array_equal(back[k], v), k
+    return m
+
+
+def synth_token_rows(cfg: C.EncoderConfig, seed: int, lengths, max_len: int):
+    """Right-padded token rows as the tokenizer emits them: <s>=0 ... </s>=2, pad = cfg.pad_token_id."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    for n in lengths:
+        body = rng.integers(3, cfg.vocab_size, size=max(0, n - 2))
+        rows.append([0] + [int(v) for v in body] + [2] + [cfg.pad_token_id] * (max_len - n))
+    return rows
+
+
+def golden_roberta(cfg_name: str, lengths, max_len=80, seed=0, atol=2e-4):
+    cfg = C.get_config(cfg_name)
+    print(f"[{cfg.name}] generating weights (seed {seed})")
+    w = random_init(cfg, seed)
+    m = hf_roberta(cfg, w)
+    rows = synth_token_rows(cfg, 7, lengths, max_len)
+    ids = torch.tensor(rows, dtype=torch.long)
+    mask = ids.ne(cfg.pad_token_id).long()
+    with torch.no_grad():
+        res = m(input_ids=ids, attention_mask=mask, output_hidden_states=True)
+    out = {"lengths": np.asarray(lengths, dtype=np.int64), "max_len": np.int64(max_len), "seed": np.int64(seed), "ids_seed": np.int64(7)}
+    for j, n in enumerate(lengths):
+        hs_hf = [h[j] for h in res.hidden_states]
+        hs_or = O.roberta_hidden_states(cfg, w, rows[j])
+        assert len(hs_hf) == len(hs_or) == cfg.num_hidden_layers + 1
+        scale = max(float(h.abs().max()) for h in hs_hf)
+        worst = max(float((a - b).abs().max()) for a, b in zip(hs_or, hs_hf))
+        print(f"  row {j} ({n} tokens of {max_len}): max |oracle - HF| = {worst:.3e} (max |HF| = {scale:.2f})")
+        assert worst <= atol * max(1.0, scale), worst
+        out[f"pooled_{j}"] = np.stack([h[:n].mean(0).numpy() for h in hs_hf]).astype(np.float32)      # over the non-pad tokens
+        out[f"pooled_all_{j}"] = np.stack([h.mean(0).numpy() for h in hs_hf]).astype(np.float32)     # over all max_len rows (pads included)
+        out[f"last_{j}"] = hs_hf[-1][[0, 1, n - 1, max_len - 1]].numpy().astype(np.float32)          # <s>, first token, </s>, last (pad) row
+        out[f"meanlast4_{j}"] = torch.mean(torch.stack(hs_hf[-4:]), 0)[[0, n - 1, max_len - 1]].numpy().astype(np.float32)
+    path = os.path.join(GOLDEN, cfg.name.replace("/", "__") + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"  wrote {path}")
+
+
 def pooled_all(hs) -> np.ndarray:
     return np.stack([h.reshape(-1, h.shape[-1]).mean(dim=0).numpy() for h in hs])
 
@@ -134,12 +204,33 @@ def check_close(name, a, b, atol):
     return err
 
 
-def golden_w2v(cfg_name: str, lengths, seed=0, atol=2e-4):
+OUTLIER_CHANNELS = (7, 300, 511, 900)
+
+
+def outlier_init(cfg: C.EncoderConfig, seed: int = 0):
+    """random_init with the residual-stream statistics of a trained checkpoint grafted on (all weights
+    are N(0, 0.02), real WavLM / Whisper checkpoints carry channels 10^2-10^3 above the rest): four output channels
+    of the feature projection are scaled x300, so those channels of the fp32 residual stream dominate every
+    LayerNorm's statistics from hidden state 0 on, and one LayerNorm gain in the middle of the stack is scaled x20.
+    Deterministic; test infrastructure only (the product never calls it)."""
+    w = random_init(cfg, seed)
+    ch = [c for c in OUTLIER_CHANNELS if c < cfg.hidden_size]
+    fw, fb = w["featproj.weight"].copy(), w["featproj.bias"].copy()
+    fw[ch, :] *= 300.0
+    fb[ch] *= 300.0
+    w["featproj.weight"], w["featproj.bias"] = fw, fb
+    g = w[f"layer{cfg.num_hidden_layers // 2}.ln1.weight"].copy()
+    g[ch[0]] *= 20.0
+    w[f"layer{cfg.num_hidden_layers // 2}.ln1.weight"] = g
+    return w
+
+
+def golden_w2v(cfg_name: str, lengths, seed=0, atol=2e-4, suffix="", init=None):
     import transformers as tr
 
     cfg = C.get_config(cfg_name)
-    print(f"[{cfg.name}] generating weights (seed {seed})")
-    w = random_init(cfg, seed)
+    print(f"[{cfg.name}{suffix}] generating weights (seed {seed})")
+    w = (init or random_init)(cfg, seed)
     m = hf_model(cfg, w)
     fe = tr.Wav2Vec2FeatureExtractor(feature_size=1, sampling_rate=16000, padding_value=0.0, do_normalize=True, return_attention_mask=True)
     out = {"lengths": np.asarray(lengths, dtype=np.int64), "seed": np.int64(seed), "wave_seed_base": np.int64(7)}
@@ -163,7 +254,7 @@ def golden_w2v(cfg_name: str, lengths, seed=0, atol=2e-4):
         out[f"pooled_{j}"] = pooled_all(hs_hf).astype(np.float32)          # [L+1, d] masked mean of every hidden state
         out[f"last_{j}"] = hs_hf[-1][:4].numpy().astype(np.float32)         # first 4 frames of last_hidden_state
         out[f"meanlast4_pooled_{j}"] = torch.mean(torch.stack(hs_hf[-4:]), 0).mean(0).numpy().astype(np.float32)
-    path = os.path.join(GOLDEN, cfg.name.replace("/", "__") + ".npz")
+    path = os.path.join(GOLDEN, cfg.name.replace("/", "__") + suffix + ".npz")
     np.savez_compressed(path, **out)
     print(f"  wrote {path}")
 
@@ -276,6 +367,8 @@ def main():
     for name in ("tiny/whisper", "tiny/whisper128"):
         if want(name):
             golden_whisper(name, [16000, 80000, 480000, 496000])
+    if want("tiny/roberta"):
+        golden_roberta("tiny/roberta", [80, 2, 3, 17, 64, 65], max_len=80)
     if args.full:
         if want("microsoft/wavlm-large"):
             golden_w2v("microsoft/wavlm-large", [4001, 64000, 192000], atol=5e-4)
@@ -285,6 +378,19 @@ def main():
             golden_w2v("facebook/hubert-xlarge-ls960-ft", [4001, 96000], atol=5e-4)
         if want("facebook/wav2vec2-xls-r-2b"):
             golden_w2v("facebook/wav2vec2-xls-r-2b", [4001, 96000], atol=5e-4)
+        if want("roberta-large"):
+            golden_roberta("roberta-large", [80, 9, 33], max_len=80, atol=5e-4)
+        # benched lengths: 20 s = 999 frames for WavLM-large (configs[4]'s longest; multi-tile bias
+        # window at full size), 8 s = 399 frames for the wide-head models (configs[3])
+        if want("long/microsoft/wavlm-large"):
+            golden_w2v("microsoft/wavlm-large", [320000], atol=5e-4, suffix="__long")
+        if want("long/facebook/hubert-xlarge-ls960-ft"):
+            golden_w2v("facebook/hubert-xlarge-ls960-ft", [128000], atol=5e-4, suffix="__long")
+        if want("long/facebook/wav2vec2-xls-r-2b"):
+            golden_w2v("facebook/wav2vec2-xls-r-2b", [128000], atol=5e-4, suffix="__long")
+        # trained-checkpoint statistics: outlier channels in the residual stream (see outlier_init)
+        if want("outlier/microsoft/wavlm-large"):
+            golden_w2v("microsoft/wavlm-large", [64000, 17777], atol=5e-4, suffix="__outlier", init=outlier_init)
 
 
 if __name__ == "__main__":

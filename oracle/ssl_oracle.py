@@ -123,8 +123,10 @@ def wavlm_position_bias(cfg, w: W, T: int) -> torch.Tensor:
     return _t(w["rel_attn_embed"])[bucket].permute(2, 0, 1)
 
 
-def self_attention(cfg, w: W, li: int, h: torch.Tensor, bias: torch.Tensor | None, whisper: bool = False) -> torch.Tensor:
-    """Multi-head self-attention for one utterance (no padding, so no key mask).
+def self_attention(cfg, w: W, li: int, h: torch.Tensor, bias: torch.Tensor | None, whisper: bool = False,
+                   n_keys: int | None = None) -> torch.Tensor:
+    """Multi-head self-attention for one utterance (no padding, so no key mask; n_keys: the text encoder's padded
+    sequences, where keys >= n_keys carry the -inf additive mask, HF RobertaSelfAttention modeling_roberta.py:190-254).
     wav2vec2/HuBERT: Wav2Vec2Attention (HF models/wav2vec2/modeling_wav2vec2.py:438-549);
     WavLM: torch MHA with the gated relative position bias as additive float mask (HF modeling_wavlm.py:147-228):
         gate_a, gate_b = sigmoid(gru_rel_pos_linear(x_head).view(2, 4).sum(-1));  g = a * (b * const - 1) + 2
@@ -150,6 +152,8 @@ def self_attention(cfg, w: W, li: int, h: torch.Tensor, bias: torch.Tensor | Non
         const = _t(w[f"layer{li}.gru.const"]).view(H, 1)
         g = ga * (gb * const - 1.0) + 2.0                                           # [H, T]
         scores = scores + g[:, :, None] * bias
+    if n_keys is not None and n_keys < T:
+        scores[:, :, n_keys:] = float("-inf")
     p = torch.softmax(scores, dim=-1)
     o = (p @ v).transpose(0, 1).reshape(T, d)
     return F.linear(o, _t(w[f"layer{li}.o.weight"]), _t(w[f"layer{li}.o.bias"]))
@@ -167,25 +171,25 @@ def encoder_layer(cfg, w: W, li: int, x: torch.Tensor, bias, whisper: bool = Fal
     return x + F.linear(h, _t(w[f"layer{li}.fc2.weight"]), _t(w[f"layer{li}.fc2.bias"]))
 
 
-def encoder_layer_post_ln(cfg, w: W, li: int, x: torch.Tensor, bias) -> torch.Tensor:
+def encoder_layer_post_ln(cfg, w: W, li: int, x: torch.Tensor, bias, n_keys: int | None = None) -> torch.Tensor:
     """Post-LN block of the base-size checkpoints (WavLMEncoderLayer, HF modeling_wavlm.py:298-336; Wav2Vec2EncoderLayer,
     modeling_wav2vec2.py:576-609):  x = LN1(x + Attn(x));  x = LN2(x + FFN(x))."""
     d = x.shape[-1]
-    x = x + self_attention(cfg, w, li, x, bias)
+    x = x + self_attention(cfg, w, li, x, bias, n_keys=n_keys)
     x = F.layer_norm(x, (d,), _t(w[f"layer{li}.ln1.weight"]), _t(w[f"layer{li}.ln1.bias"]), cfg.layer_norm_eps)
     h = F.gelu(F.linear(x, _t(w[f"layer{li}.fc1.weight"]), _t(w[f"layer{li}.fc1.bias"])))
     x = x + F.linear(h, _t(w[f"layer{li}.fc2.weight"]), _t(w[f"layer{li}.fc2.bias"]))
     return F.layer_norm(x, (d,), _t(w[f"layer{li}.ln2.weight"]), _t(w[f"layer{li}.ln2.bias"]), cfg.layer_norm_eps)
 
 
-def run_stack_post_ln(cfg, w: W, x: torch.Tensor, bias) -> List[torch.Tensor]:
+def run_stack_post_ln(cfg, w: W, x: torch.Tensor, bias, n_keys: int | None = None) -> List[torch.Tensor]:
     """WavLMEncoder / Wav2Vec2Encoder (do_stable_layer_norm=False; HF modeling_wavlm.py:376-447): the encoder LayerNorm
     comes right after the positional conv, [0] = its output, [i] = output of layer i (already normalised)."""
     d = x.shape[-1]
     x = F.layer_norm(x, (d,), _t(w["final_ln.weight"]), _t(w["final_ln.bias"]), cfg.layer_norm_eps)
     hs = [x]
     for li in range(cfg.num_hidden_layers):
-        x = encoder_layer_post_ln(cfg, w, li, x, bias)
+        x = encoder_layer_post_ln(cfg, w, li, x, bias, n_keys)
         hs.append(x)
     return hs
 
@@ -248,6 +252,30 @@ def whisper_hidden_states(cfg, w: W, mel: torch.Tensor) -> List[torch.Tensor]:
     h = F.gelu(F.conv1d(h, _t(w["conv2.weight"]), _t(w["conv2.bias"]), stride=2, padding=1))
     h = h[0].transpose(0, 1) + _t(w["embed_positions"])
     return run_stack(cfg, w, h, None, whisper=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# RoBERTa (text branch: preprocessing/preprocess_roberta.py:48-74)
+# --------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def roberta_hidden_states(cfg, w: W, input_ids: Sequence[int], n_valid: int | None = None) -> List[torch.Tensor]:
+    """RobertaModel(input_ids, attention_mask, output_hidden_states=True) for ONE right-padded sequence
+    (HF models/roberta/modeling_roberta.py: RobertaEmbeddings :56-159, RobertaSelfAttention :190-254, RobertaSelfOutput
+    :334-345, RobertaIntermediate :377-389, RobertaOutput :392-403, RobertaLayer :406-468, RobertaEncoder :497-526).
+    Embeddings: word[ids] + type[0] + position[pad + cumsum(ids != pad) * (ids != pad)] -> LayerNorm = hidden_states[0];
+    every layer is post-LN:  x = LN(x + SelfOutput.dense(attn(x)));  x = LN(x + Output.dense(gelu(Intermediate.dense(x)))).
+    Keys at pad positions get the -inf additive mask; ALL positions (pads included) are returned, as HF does.
+    Returns L+1 tensors [T, d]."""
+    ids = torch.as_tensor(list(input_ids), dtype=torch.long)
+    pad = cfg.pad_token_id
+    not_pad = ids.ne(pad)
+    n_ids = int(not_pad.sum())
+    if n_valid is None:
+        n_valid = n_ids
+    pos = torch.cumsum(not_pad.long(), 0) * not_pad.long() + pad
+    x = _t(w["embed.word"])[ids] + _t(w["embed.type"])[0]
+    x = x + _t(w["embed.position"])[pos]
+    return run_stack_post_ln(cfg, w, x, None, n_keys=n_valid)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 for t in "$@"; do
   name=$(echo "$t" | tr ' /' '__')
   echo "=== $t ===" | tee -a gpurun_out/diag_all.log
-  timeout 600 python tests/diag_gpu.py $t > gpurun_out/diag_$name.log 2>&1
+  timeout 600 python tools/diag_gpu.py $t > gpurun_out/diag_$name.log 2>&1
   echo "exit=$?" >> gpurun_out/diag_$name.log
   tail -n 60 gpurun_out/diag_$name.log | tee -a gpurun_out/diag_all.log
 done

@@ -1,5 +1,5 @@
 """Dev tool: time the tcgen05 GEMM entry point against torch.matmul (cuBLAS) on a list of shapes.
-    python tests/bench_gemm.py            (SERENC_FORCE_1CTA=1 to force the single-CTA kernel)"""
+    python tools/bench_gemm.py            (SERENC_FORCE_1CTA=1 to force the single-CTA kernel)"""
 import os, sys, time
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -3,7 +3,7 @@
 Not a pytest module — a bring-up tool that prints numbers instead of asserting, one sub-command per process so
 that a device-side trap in one kernel cannot poison the others:
 
-    python tests/diag_gpu.py gemm | conv | grouped | ln | attn | model <cfg> | logmel | whisper <cfg>
+    python tools/diag_gpu.py gemm | conv | grouped | ln | attn | model <cfg> | logmel | whisper <cfg>
 """
 from __future__ import annotations
 
