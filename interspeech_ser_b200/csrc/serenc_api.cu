@@ -21,6 +21,9 @@
 #include "attention_params.cuh"
 #include "attention_tc.cuh"
 #include "attention_tc_wide.cuh"
+#ifdef SERENC_AB_ARMS
+#include "attention_tc_split.cuh"
+#endif
 #include "common.cuh"
 #include "frontend_norm.cuh"
 #include "gemm_tcgen05.cuh"
@@ -126,6 +129,7 @@ struct serenc_handle {
   bool no_posconv_slab = false;   // positional conv through the generic implicit GEMM
   bool force_mma_sync_attn = false;  // attention on the mma.sync kernel
   int attn_deep64 = 0;               // bias-free head_dim-64 attention on the deep-pipelined kernel
+  bool attn_split = false;           // head_dim-64 attention on the two-threads-per-row kernel (attention_tc_split.cuh)
   int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
@@ -590,8 +594,35 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
                 cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
   ProfScope ps(h, SERENC_PROF_ATTENTION, 1, alg_flops, 0.0, st);
+#ifdef SERENC_AB_ARMS
+  if (h->head_dim == 64 && !h->force_mma_sync_attn && h->attn_split) {
+    // measured dead end kept as an A/B arm (attention_tc_split.cuh): Q and P in TMEM, two softmax threads per query row
+    CUtensorMap tmkv;
+    AttnParams pt = p;
+    pt.trace = h->gemm_trace;
+    pt.heads = h->cfg.heads; pt.batch = batch;
+    SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
+    const size_t smem = fs_smem_bytes(wavlm, tmax);
+    if (smem > (size_t)FA_SMEM_LIMIT) SERENC_FAIL(SERENC_ERR_INVALID, "attention: utterance of %d frames exceeds the bias-window capacity", tmax);
+    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FS_THREADS);
+    if (wavlm) {
+      if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
+      if (!p.gate_ready) {   // stand-alone entry (serenc_op_attention); the encoder stacks fuse the gate into the LayerNorm
+        const int64_t nthr = sum_rows * h->cfg.heads;
+        wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
+        SERENC_CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+      }
+      attention_tc_split_kernel<true><<<grid, block, smem, st>>>(tmkv, pt);
+    } else {
+      attention_tc_split_kernel<false><<<grid, block, smem, st>>>(tmkv, pt);
+    }
+    SERENC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+#endif
   if (h->head_dim == 64 && !h->force_mma_sync_attn && (wavlm || !h->attn_deep64)) {
-    // tcgen05 path: Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
+    // first-generation tcgen05 path (A/B arm): Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
     CUtensorMap tmq, tmkv;
     AttnParams pt = p;
     pt.trace = h->gemm_trace;
@@ -831,6 +862,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_DEEP64"); if (e) h->attn_deep64 = e[0] == '1'; }
+  { const char* e = getenv("SERENC_ATTN_SPLIT"); h->attn_split = e && e[0] == '1'; }
 #endif
   *out = h;
 
@@ -895,6 +927,10 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
 #endif
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+#ifdef SERENC_AB_ARMS
+    attr(cudaFuncSetAttribute(attention_tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_FIXED));
+#endif
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));

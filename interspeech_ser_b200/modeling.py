@@ -420,7 +420,9 @@ class WhisperModel(_Base):
     @torch.no_grad()
     def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
                        want_frames: bool = False, want_pooled: bool = True, literal_crop: bool = True,
-                       layer_weights: Optional[Sequence[float]] = None, layers: Optional[Sequence[int]] = None) -> Extracted:
+                       layer_weights: Optional[Sequence[float]] = None, layers: Optional[Sequence[int]] = None,
+                       use_graph: Optional[bool] = None) -> Extracted:
+        # use_graph is accepted for signature parity with SpeechEncoderModel and ignored: a 30 s window is never launch-bound
         starts, off = [], 0
         for n in lens:
             starts.append(off)
