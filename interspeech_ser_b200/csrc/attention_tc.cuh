@@ -68,6 +68,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for x <= 0 on the FMA pipe, two values at once: x = n + f with n = round(x) (magic-number add), 2^f by a cubic
+// (|f| <= 0.5, max relative error ~1e-4: below the bf16 rounding of P), n added into the exponent field by one LEA.
+// Used for a share of a thread's exponentials when the MUFU pipe (one ex2 per 8 cycles, warp and scheduler) is the
+// bound of the softmax.
+__device__ __forceinline__ void exp2_fma2(float x0, float x1, float& y0, float& y1) {
+  const float MAGIC = 12582912.f;   // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = pack_f32x2(x0, x1);
+  const uint64_t r = fadd2(x, pack_f32x2(MAGIC, MAGIC));                 // low mantissa bits = round(x)
+  const uint64_t f = fadd2(x, fadd2(pack_f32x2(MAGIC, MAGIC), fmul2(r, pack_f32x2(-1.f, -1.f))));   // x - round(x)
+  uint64_t p = pack_f32x2(0.0555041f, 0.0555041f);
+  p = ffma2(p, f, pack_f32x2(0.2402265f, 0.2402265f));
+  p = ffma2(p, f, pack_f32x2(0.6931472f, 0.6931472f));
+  p = ffma2(p, f, pack_f32x2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(r, r0, r1);
+  y0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  y1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
 __device__ __forceinline__ void softmax_group_sync() {  // the 128 softmax threads only (named barrier 1)
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
@@ -121,7 +142,10 @@ wavlm_gate_kernel(const bf16* __restrict__ hln, int64_t rows, int d, int heads, 
   gate[i] = ga * (gb * __ldg(gru_const + h) - 1.f) + 2.f;
 }
 
-template <bool WAVLM>
+// POLY > 0: every POLY-th pair of a thread's exponentials runs on the FMA pipe (exp2_fma2) instead of MUFU.
+// CTLHINT: the control warp's long waits (P_j ready) suspend with a time hint instead of spinning: the four control
+// warps of an SM all sit on scheduler 0 (warp id 4), next to the first softmax warp of every CTA.
+template <bool WAVLM, int POLY = 0, bool CTLHINT = false>
 __global__ void __launch_bounds__(FA_THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t fa_smem_raw[];
@@ -242,6 +266,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_2d(sK, &tmKV, bar_k, colk, r0u + (j + 1) * FA_BN);
         }
         __syncwarp();
+        if (CTLHINT) mbar_wait_relaxed<500>(bar_p, ph); else
         mbar_wait(bar_p, ph);  // P_j in shared memory, every softmax thread is done reading S_j, O rescaled
         if (j < 4) fa_stamp(tr, 5 + 4 * j);
         tc_fence_after();
@@ -391,7 +416,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t x2 = WAVLM ? fadd2(s2, negm2) : ffma2(s2, sc22, negm2);
           float x0, x1;
           unpack_f32x2(x2, x0, x1);
-          float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+          float e0, e1;
+          constexpr int PM = POLY > 0 ? POLY : 1;
+          if (POLY > 0 && ((k >> 1) % PM) == PM - 1) {
+            exp2_fma2(x0, x1, e0, e1);
+          } else {
+            e0 = fast_exp2(x0);
+            e1 = fast_exp2(x1);
+          }
           if (!FULLC) {
             if (c * 32 + k >= ncols) e0 = 0.f;
             if (c * 32 + k + 1 >= ncols) e1 = 0.f;

@@ -62,7 +62,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 
-template <int HD>
+template <int HD, bool CTLHINT = false>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   using C = FawCfg<HD>;
@@ -192,6 +192,7 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         __syncwarp();
       }
       if (j < 4) fa_stamp(tr, 4 + 4 * j);
+      if (CTLHINT) mbar_wait_relaxed<500>(bar_p, (uint32_t)(j & 1)); else
       mbar_wait(bar_p, (uint32_t)(j & 1));   // P_j in TMEM (over S_j), O rescaled
       if (j < 4) fa_stamp(tr, 5 + 4 * j);
       mbar_wait(bar_v + sl, ph2);

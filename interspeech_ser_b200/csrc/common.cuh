@@ -95,8 +95,36 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(-a, e, hx + a);
 }
 
-// two GELUs at once: the polynomial runs on FFMA2 (7 packed instead of 14 scalar FMAs); same arithmetic per lane as
-// gelu_erf_fast, so results are bit-identical to it
+// The form every epilogue and row kernel uses since round 2 (two values at once):
+//   gelu(x) = h + h * tanh(x * (B1 + B3 x^2 + B5 x^4)),  h = x / 2,  x^2 clamped at 64
+// (B1, B3, B5) = minimax fit of the exact erf GELU (oracle/gelu_fit.py): max |error| 2.5e-5 from the fit plus the
+// 2^-11 relative error of MUFU.TANH, i.e. <= 2.5e-4 |x| - an order of magnitude below the bf16 rounding (2^-9 relative)
+// every one of these results goes through. Measured on the oracle (oracle/gelu_fit.py --model): replacing F.gelu by
+// this form, tanh noise included, moves WavLM-large's pooled embeddings by 1e-4 (max relative), cosine 0.9999998.
+// The clamp keeps the argument monotone: B5 < 0 would turn the polynomial over beyond |x| = 10.
+// 6 packed FP32 instructions + 2 FMNMX + 2 MUFU per pair, against ~19 for the erf-exact form below: the GELU was ~10 of
+// the ~22 instructions per element of conv0 and the conv LayerNorm passes (issue-bound), and 9 % of an FC1 launch.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& y0, float& y1) {
+  const uint64_t x = pack_f32x2(x0, x1);
+  float q0, q1;
+  unpack_f32x2(fmul2(x, x), q0, q1);
+  const uint64_t x2 = pack_f32x2(fminf(q0, 64.f), fminf(q1, 64.f));
+  uint64_t u = ffma2(x2, pack_f32x2(-3.515174775e-04f, -3.515174775e-04f), pack_f32x2(3.700565057e-02f, 3.700565057e-02f));
+  u = ffma2(u, x2, pack_f32x2(7.975078789e-01f, 7.975078789e-01f));
+  float u0, u1;
+  unpack_f32x2(fmul2(u, x), u0, u1);
+  const uint64_t t = pack_f32x2(tanh_approx(u0), tanh_approx(u1));
+  const uint64_t h = fmul2(x, pack_f32x2(0.5f, 0.5f));
+  unpack_f32x2(ffma2(h, t, h), y0, y1);
+}
+
+// two erf-exact GELUs at once (the round-1 form, kept for op-level comparisons): the polynomial runs on FFMA2 (7 packed
+// instead of 14 scalar FMAs); same arithmetic per lane as gelu_erf_fast, so results are bit-identical to it
 __device__ __forceinline__ void gelu_erf_fast2(float x0, float x1, float& y0, float& y1) {
   const float t0 = fminf(fmaf(fabsf(x0), 0.35355339059327373f, -1.0f), 1.0f);
   const float t1 = fminf(fmaf(fabsf(x1), 0.35355339059327373f, -1.0f), 1.0f);
@@ -327,6 +355,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 16 lanes x 32 consecutive fp32 columns in the "16x256b" fragment shape (the mma.sync C-fragment layout): thread t receives,
+// for every 8-column group g = 0..3, r[4g], r[4g+1] = columns 8g + 2(t%4), +1 of TMEM lane (lane_base + t/4) and
+// r[4g+2], r[4g+3] = the same columns of lane (lane_base + t/4 + 8). Four consecutive threads therefore hold 32
+// contiguous bytes of one row: global accesses straight from this layout touch whole 32-byte sectors, no
+// shared-memory transpose needed (cross-checked against cute/atom/copy_traits_sm100.hpp, SM100_TMEM_LOAD_16dp256b4x).
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

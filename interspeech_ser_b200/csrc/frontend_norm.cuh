@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const void* __restrict__ 
         const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
         float v0, v1, y0, y1;
         unpack_f32x2(ffma2(a[i], pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), v0, v1);
-        gelu_erf_fast2(v0, v1, y0, y1);
+        gelu_fast2(v0, v1, y0, y1);
         orow[32 * i + lane] = pack_bf16x2(y0, y1);
       }
       continue;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256, 1) conv0_kernel(const void* __restrict__ 
       const float2 g = s_g[32 * i + lane], be = s_be[32 * i + lane];
       float v0, v1, y0, y1;
       unpack_f32x2(ffma2(fmul2(a[i], rs2), pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), v0, v1);
-      gelu_erf_fast2(v0, v1, y0, y1);
+      gelu_fast2(v0, v1, y0, y1);
       orow[32 * i + lane] = pack_bf16x2(y0, y1);
     }
   }
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
       unpack_f32x2(ffma2(fmul2(fadd2(pack_f32x2(v[r][i].x, v[r][i].y), nmu2), rs2), pack_f32x2(g.x, g.y), pack_f32x2(be.x, be.y)), o.x, o.y);
       unpack_f32x2(ffma2(fmul2(fadd2(pack_f32x2(v[r][i].z, v[r][i].w), nmu2), rs2), pack_f32x2(g.z, g.w), pack_f32x2(be.z, be.w)), o.z, o.w);
       if (GELU) {
-        gelu_erf_fast2(o.x, o.y, o.x, o.y);
-        gelu_erf_fast2(o.z, o.w, o.z, o.w);
+        gelu_fast2(o.x, o.y, o.x, o.y);
+        gelu_fast2(o.z, o.w, o.z, o.w);
       }
       store4<TOut>(out + orow[r] * ld_out + c, o);
       if (out2) store4<bf16>(out2 + orow[r] * ld_out2 + c, o);

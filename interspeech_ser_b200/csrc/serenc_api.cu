@@ -22,6 +22,7 @@
 #include "attention_tc.cuh"
 #include "attention_tc_wide.cuh"
 #ifdef SERENC_AB_ARMS
+#include "attention_tc_v3.cuh"
 #include "attention_tc_split.cuh"
 #endif
 #include "common.cuh"
@@ -130,6 +131,8 @@ struct serenc_handle {
   bool force_mma_sync_attn = false;  // attention on the mma.sync kernel
   int attn_deep64 = 0;               // bias-free head_dim-64 attention on the deep-pipelined kernel
   bool attn_split = false;           // head_dim-64 attention on the two-threads-per-row kernel (attention_tc_split.cuh)
+  bool attn_v3 = false;              // attention on the one-pass / Q-in-TMEM kernel (attention_tc_v3.cuh)
+  int attn_variant = 0;              // bit 0: control-warp waits suspend instead of spinning; bit 1: every 4th pair of exponentials on the FMA pipe; 4: every 2nd + suspend
   int max_smem = 227 * 1024;      // opt-in dynamic shared memory per CTA
   struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; int n; };
   std::vector<ProfRec> recs;
@@ -594,68 +597,112 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
                 cudaStream_t st) {
   if (batch <= 0 || tmax <= 0) return 0;
   ProfScope ps(h, SERENC_PROF_ATTENTION, 1, alg_flops, 0.0, st);
-#ifdef SERENC_AB_ARMS
-  if (h->head_dim == 64 && !h->force_mma_sync_attn && h->attn_split) {
-    // measured dead end kept as an A/B arm (attention_tc_split.cuh): Q and P in TMEM, two softmax threads per query row
+  AttnParams pt = p;
+  pt.trace = h->gemm_trace;
+  pt.heads = h->cfg.heads; pt.batch = batch;
+  const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
+  auto ensure_gate = [&]() -> int {   // stand-alone entry (serenc_op_attention); the encoder stacks fuse the gate into the LayerNorm
+    if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
+    if (!p.gate_ready) {
+      const int64_t nthr = sum_rows * h->cfg.heads;
+      wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
+      SERENC_CUDA_OK(cudaGetLastError());
+      h->launches += 1;
+    }
+    return 0;
+  };
+#ifdef SERENC_AB_ARMS   // measured alternatives, development build only (profiles/r02_notes.md)
+  if (h->force_mma_sync_attn) {
+    switch (h->head_dim) {
+      case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
+      case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
+      case 120: return launch_attn_hd<120>(p, wavlm, tmax, h->cfg.heads, batch, st);
+    }
+  }
+  if (h->head_dim == 64 && h->attn_split) {   // two softmax threads per query row, Q and P in TMEM (attention_tc_split.cuh)
     CUtensorMap tmkv;
-    AttnParams pt = p;
-    pt.trace = h->gemm_trace;
-    pt.heads = h->cfg.heads; pt.batch = batch;
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
     const size_t smem = fs_smem_bytes(wavlm, tmax);
-    if (smem > (size_t)FA_SMEM_LIMIT) SERENC_FAIL(SERENC_ERR_INVALID, "attention: utterance of %d frames exceeds the bias-window capacity", tmax);
-    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FS_THREADS);
     if (wavlm) {
-      if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
-      if (!p.gate_ready) {   // stand-alone entry (serenc_op_attention); the encoder stacks fuse the gate into the LayerNorm
-        const int64_t nthr = sum_rows * h->cfg.heads;
-        wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
-        SERENC_CUDA_OK(cudaGetLastError());
-        h->launches += 1;
-      }
-      attention_tc_split_kernel<true><<<grid, block, smem, st>>>(tmkv, pt);
+      SERENC_TRY(ensure_gate());
+      attention_tc_split_kernel<true><<<grid, dim3(FS_THREADS), smem, st>>>(tmkv, pt);
     } else {
-      attention_tc_split_kernel<false><<<grid, block, smem, st>>>(tmkv, pt);
+      attention_tc_split_kernel<false><<<grid, dim3(FS_THREADS), smem, st>>>(tmkv, pt);
+    }
+    SERENC_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (h->attn_v3 && (h->head_dim == 64 || !wavlm)) {   // one-pass softmax, Q in TMEM, 2 CTAs/SM for every head_dim (attention_tc_v3.cuh)
+    CUtensorMap tmq, tmkv;
+    SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
+    SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
+    if (h->head_dim == 64) {
+      const size_t smem = fa3_smem_bytes<64>(wavlm, tmax);
+      if (wavlm) {
+        SERENC_TRY(ensure_gate());
+        attention_tc_v3_kernel<64, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+      } else if (h->attn_variant & 2) {
+        attention_tc_v3_kernel<64, false, 4><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+      } else {
+        attention_tc_v3_kernel<64, false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+      }
+    } else if (h->head_dim == 80) {
+      attention_tc_v3_kernel<80, false><<<grid, block, Fa3Cfg<80>::SMEM_FIXED, st>>>(tmq, tmkv, pt);
+    } else {
+      attention_tc_v3_kernel<120, false><<<grid, block, Fa3Cfg<120>::SMEM_FIXED, st>>>(tmq, tmkv, pt);
     }
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
 #endif
-  if (h->head_dim == 64 && !h->force_mma_sync_attn && (wavlm || !h->attn_deep64)) {
-    // first-generation tcgen05 path (A/B arm): Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
+  if (h->head_dim == 64 && (wavlm || !h->attn_deep64)) {
+    // head_dim 64 (attention_tc.cuh): Q/K/V tiles through one tensor map over the packed [sum_T, 3d] projection buffer
     CUtensorMap tmq, tmkv;
-    AttnParams pt = p;
-    pt.trace = h->gemm_trace;
-    pt.heads = h->cfg.heads; pt.batch = batch;
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
     SERENC_TRY(get_tmap(h, p.qkv, (uint64_t)p.ld_qkv, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
     const size_t smem = fa_smem_bytes(wavlm, tmax);
     if (smem > FA_SMEM_LIMIT) SERENC_FAIL(SERENC_ERR_INVALID, "attention: utterance of %d frames exceeds the bias-window capacity", tmax);
-    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
-    if (wavlm) {
-      if (!p.gate) SERENC_FAIL(SERENC_ERR_STATE, "attention: no gate buffer");
-      if (!p.gate_ready) {   // stand-alone entry (serenc_op_attention); the encoder stacks fuse the gate into the LayerNorm
-        const int64_t nthr = sum_rows * h->cfg.heads;
-        wavlm_gate_kernel<<<(unsigned)ceil_div64(nthr, 256), 256, 0, st>>>(p.hln, sum_rows, p.d, h->cfg.heads, p.gru_w, p.gru_b, p.gru_const, p.gate);
-        SERENC_CUDA_OK(cudaGetLastError());
-        h->launches += 1;
-      }
-      attention_tc_kernel<true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
-    } else {
-      attention_tc_kernel<false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+    if (wavlm) SERENC_TRY(ensure_gate());
+    switch (h->attn_variant) {
+#ifdef SERENC_AB_ARMS
+      case 1:
+        if (wavlm) attention_tc_kernel<true, 0, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        else attention_tc_kernel<false, 0, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        break;
+      case 2:
+        if (wavlm) attention_tc_kernel<true, 4, false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        else attention_tc_kernel<false, 4, false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        break;
+      case 3:
+        if (wavlm) attention_tc_kernel<true, 4, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        else attention_tc_kernel<false, 4, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        break;
+      case 4:
+        if (wavlm) attention_tc_kernel<true, 2, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        else attention_tc_kernel<false, 2, true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        break;
+#endif
+      default:
+        if (wavlm) attention_tc_kernel<true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        else attention_tc_kernel<false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
     }
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
-  if ((h->head_dim == 80 || h->head_dim == 120 || h->head_dim == 64) && !wavlm && !h->force_mma_sync_attn) {
-    // tcgen05 path for wide heads: rank-3 {head_dim, 3 * heads, rows} maps (zero fill past the head's last column)
+  if ((h->head_dim == 80 || h->head_dim == 120 || h->head_dim == 64) && !wavlm) {
+    // wide heads (attention_tc_wide.cuh): rank-3 {head_dim, 3 * heads, rows} maps (zero fill past the head's last column)
     CUtensorMap tmq, tmkv;
-    AttnParams pt = p;
-    pt.trace = h->gemm_trace;
-    pt.heads = h->cfg.heads; pt.batch = batch;
     SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BM, &tmq));
     SERENC_TRY(get_tmap_heads(h, p.qkv, (uint64_t)h->head_dim, (uint64_t)3 * h->cfg.heads, (uint64_t)sum_rows, (uint64_t)p.ld_qkv * 2, FA_BN, &tmkv));
-    const dim3 grid(ceil_div(tmax, FA_BM), h->cfg.heads, batch), block(FA_THREADS);
+#ifdef SERENC_AB_ARMS
+    if (h->attn_variant & 1) {
+      if (h->head_dim == 80) attention_tc_wide_kernel<80, true><<<grid, block, FawCfg<80>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      else if (h->head_dim == 64) attention_tc_wide_kernel<64, true><<<grid, block, FawCfg<64>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      else attention_tc_wide_kernel<120, true><<<grid, block, FawCfg<120>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      SERENC_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+#endif
     if (h->head_dim == 80)
       attention_tc_wide_kernel<80><<<grid, block, FawCfg<80>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
     else if (h->head_dim == 64)
@@ -665,13 +712,6 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
-#ifdef SERENC_AB_ARMS
-  switch (h->head_dim) {
-    case 64: return launch_attn_hd<64>(p, wavlm, tmax, h->cfg.heads, batch, st);
-    case 80: return launch_attn_hd<80>(p, wavlm, tmax, h->cfg.heads, batch, st);
-    case 120: return launch_attn_hd<120>(p, wavlm, tmax, h->cfg.heads, batch, st);
-  }
-#endif
   SERENC_FAIL(SERENC_ERR_INVALID, "attention: head_dim %d %s the gated relative position bias is not supported", h->head_dim,
               wavlm ? "with" : "without");
 }
@@ -863,6 +903,8 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_DEEP64"); if (e) h->attn_deep64 = e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_SPLIT"); h->attn_split = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_ATTN_V3"); h->attn_v3 = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_ATTN_VARIANT"); h->attn_variant = e ? atoi(e) : 0; }
 #endif
   *out = h;
 
@@ -927,13 +969,29 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
 #endif
     attr(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
-#ifdef SERENC_AB_ARMS
-    attr(cudaFuncSetAttribute(attention_tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
-    attr(cudaFuncSetAttribute(attention_tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_FIXED));
-#endif
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));
+#ifdef SERENC_AB_ARMS
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_kernel<false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<64>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<80, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<80>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_wide_kernel<120, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FawCfg<120>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(attention_tc_v3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT / 2));
+    attr(cudaFuncSetAttribute(attention_tc_v3_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa3Cfg<64>::SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_v3_kernel<64, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa3Cfg<64>::SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_v3_kernel<80, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa3Cfg<80>::SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_v3_kernel<120, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa3Cfg<120>::SMEM_FIXED));
+    attr(cudaFuncSetAttribute(attention_tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
+    attr(cudaFuncSetAttribute(attention_tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_FIXED));
+#endif
     attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
     attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
   }

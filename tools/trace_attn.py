@@ -36,6 +36,8 @@ for wavlm in ((1, 0) if cfg.family == "wavlm" else (0,)):
         e0.record(); run(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(f"=== wavlm={wavlm} B={B} T={T}: {min(ts)*1000:.1f} us (min of 5; includes the tiny offsets H2D)")
+    if os.environ.get("NOTRACE"):
+        continue
     trace = torch.zeros(64 * 48, dtype=torch.int64, device=dev)
     lib.serenc_debug_gemm_trace(eng._h, trace.data_ptr())
     run(); torch.cuda.synchronize()
