@@ -359,20 +359,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-// 16 lanes x 32 consecutive fp32 columns in the "16x256b" fragment shape (the mma.sync C-fragment layout): thread t receives,
-// for every 8-column group g = 0..3, r[4g], r[4g+1] = columns 8g + 2(t%4), +1 of TMEM lane (lane_base + t/4) and
-// r[4g+2], r[4g+3] = the same columns of lane (lane_base + t/4 + 8). Four consecutive threads therefore hold 32
-// contiguous bytes of one row: global accesses straight from this layout touch whole 32-byte sectors, no
-// shared-memory transpose needed (cross-checked against cute/atom/copy_traits_sm100.hpp, SM100_TMEM_LOAD_16dp256b4x).
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // CTA-pair (cluster of 2, tcgen05 cta_group::2) variants
 // ---------------------------------------------------------------------------------------------

@@ -189,31 +189,26 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
     return;
   } else {
   // ---------------- fp32 / residual path ----------------
-  // The accumulator is read in the 16x256b fragment shape (tmem_ld_16x256b_x4): four consecutive lanes own 32 contiguous
-  // bytes of an output row, so the residual loads and the stores below touch whole 32-byte sectors straight from the
-  // registers. Round 1 transposed every 32 x 32 block through shared memory to get 128-byte-coalesced accesses; for
-  // the fp32 stream that was 256 KB of shared-memory traffic + 8 warp syncs per 128 x 256 tile and CTA, and with
-  // K = N = 1024 (the attention out-projection) the epilogue, not the mainloop, set the pace (profiles/r02_notes.md).
-  const int rin = lane >> 2;        // row inside an 8-row group
-  const int c2 = (lane & 3) * 2;    // column pair inside an 8-column group
-  int32_t orow[4];                  // output rows this lane touches: row0 + rin + 8 i (< 2^31 rows)
+  // (Round 2 measured the alternative of reading the accumulator in the 16x256b fragment shape and touching global memory
+  //  straight from it, 32-byte sectors, no shared-memory transpose: parity-green but 7-12 % SLOWER on the residual
+  //  GEMMs - 636 against 686 TFLOP/s at M = 25 472, N = K = 1 024 - because every LDG / STG then spreads over 8 lines.)
+  const int sr = lane >> 3;       // coalesced phase: sub-row 0..3
+  const int c4 = (lane & 7) * 4;  // coalesced phase: 4 consecutive columns
+  int32_t orow[8];                // output rows this lane touches in the coalesced phase (< 2^31 rows)
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t r = row0 + rin + 8 * i;
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + 4 * i + sr;
     orow[i] = -1;
     if (r < p.M) orow[i] = p.rowmap ? __ldg(p.rowmap + r) : (int32_t)r;
   }
-  float2 q[16], qn[16];             // residual values of the current / next 32-column block: [8-column group][row i]
-  auto fetch_resid = [&](float2 (&dst)[16], int col0) {
+  float4 q[8], qn[8];
+  auto fetch_resid = [&](float4 (&dst)[8], int col0) {
+    const int col = col0 + c4;
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
-      const int col = col0 + 8 * g8 + c2;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dst[g8 * 4 + i] = make_float2(0.f, 0.f);
-        if (col < p.n_per_group && orow[i] >= 0)
-          dst[g8 * 4 + i] = *reinterpret_cast<const float2*>(p.resid + (int64_t)orow[i] * p.ld_f32 + g * p.n_per_group + col);
-      }
+    for (int i = 0; i < 8; ++i) {
+      dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < p.n_per_group && orow[i] >= 0)
+        dst[i] = *reinterpret_cast<const float4*>(p.resid + (int64_t)orow[i] * p.ld_f32 + g * p.n_per_group + col);
     }
   };
   if (p.resid) fetch_resid(q, n0);
@@ -226,41 +221,49 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, float* s
   for (int c = 0; c < NCH; ++c) {
     const int col0 = n0 + c * 32;
     if (col0 < p.n_per_group) {  // warp-uniform
-      uint32_t ra[16], rb[16];   // TMEM lanes +0..15 / +16..31 of this warp's quarter
-      tmem_ld_16x256b_x4(t_addr + (uint32_t)(c * 32), ra);
-      tmem_ld_16x256b_x4(t_addr + (16u << 16) + (uint32_t)(c * 32), rb);
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
       if (p.resid && c + 1 < NCH) fetch_resid(qn, col0 + 32);
       tmem_ld_wait();
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const int col = col0 + 8 * g8 + c2;
-        if (col < p.n_per_group) {   // only multiples of 8 columns are valid (checked on the host)
-          const int gcol = g * p.n_per_group + col;
-          uint64_t bv = 0ull;        // (+0.0f, +0.0f)
-          if (p.bias) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + gcol));
-            bv = pack_f32x2(b2.x, b2.y);
-          }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(st + lane * GEMM_ST_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      __syncwarp();
+      const int col = col0 + c4;
+      if (col < p.n_per_group) {
+        const int gcol = g * p.n_per_group + col;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+        const uint64_t bv01 = pack_f32x2(bv.x, bv.y), bv23 = pack_f32x2(bv.z, bv.w);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (orow[i] < 0) continue;
-            const uint32_t (&r)[16] = (i < 2) ? ra : rb;
-            const int ri = g8 * 4 + (i & 1) * 2;
-            // packed fp32x2 adds (FADD2): the whole step runs at the power cap, every issue slot saved is clock
-            uint64_t v = fadd2(pack_f32x2(__uint_as_float(r[ri]), __uint_as_float(r[ri + 1])), bv);
-            float vx, vy;
-            unpack_f32x2(v, vx, vy);
-            if (p.act == 1) gelu_fast2(vx, vy, vx, vy);
-            if (p.resid) unpack_f32x2(fadd2(pack_f32x2(vx, vy), pack_f32x2(q[g8 * 4 + i].x, q[g8 * 4 + i].y)), vx, vy);
-            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + (int64_t)orow[i] * p.ld_f32 + gcol) = make_float2(vx, vy);
-            if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + (int64_t)orow[i] * p.ld_bf16 + gcol) = pack_bf16x2(vx, vy);
+        for (int i = 0; i < 8; ++i) {
+          if (orow[i] < 0) continue;
+          float4 v = *reinterpret_cast<const float4*>(st + (4 * i + sr) * GEMM_ST_LD + c4);
+          // packed fp32x2 adds (FADD2): the whole step runs at the power cap, every issue slot saved is clock
+          unpack_f32x2(fadd2(pack_f32x2(v.x, v.y), bv01), v.x, v.y);
+          unpack_f32x2(fadd2(pack_f32x2(v.z, v.w), bv23), v.z, v.w);
+          if (p.act == 1) {
+            gelu_fast2(v.x, v.y, v.x, v.y);
+            gelu_fast2(v.z, v.w, v.z, v.w);
+          }
+          if (p.resid) {
+            unpack_f32x2(fadd2(pack_f32x2(v.x, v.y), pack_f32x2(q[i].x, q[i].y)), v.x, v.y);
+            unpack_f32x2(fadd2(pack_f32x2(v.z, v.w), pack_f32x2(q[i].z, q[i].w)), v.z, v.w);
+          }
+          if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (int64_t)orow[i] * p.ld_f32 + gcol) = v;
+          if (p.out_bf16) {
+            uint2 u;
+            u.x = pack_bf16x2(v.x, v.y);
+            u.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(p.out_bf16 + (int64_t)orow[i] * p.ld_bf16 + gcol) = u;
           }
         }
       }
       if (p.resid) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) q[i] = qn[i];
+        for (int i = 0; i < 8; ++i) q[i] = qn[i];
       }
+      __syncwarp();
     }
   }
   }
