@@ -27,6 +27,7 @@
 #endif
 #include "common.cuh"
 #include "frontend_norm.cuh"
+#include "conv0_tc.cuh"
 #include "gemm_tcgen05.cuh"
 #include "posconv_tcgen05.cuh"
 #include "logmel.cuh"
@@ -992,6 +993,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     attr(cudaFuncSetAttribute(attention_tc_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_LIMIT));
     attr(cudaFuncSetAttribute(attention_tc_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_FIXED));
 #endif
+    attr(cudaFuncSetAttribute(conv0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0T_SMEM));
     attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
     attr(cudaFuncSetAttribute(posconv_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem));
   }
@@ -1459,6 +1461,7 @@ int make_w2v_plan(const serenc_handle* h, const int32_t* len, int batch, W2VPlan
 
 struct W2VWs {
   Conv0Utt* utts; float2* stats; int32_t* foff; int32_t* r6; int32_t *fp_gather, *gap_row, *pos_rowmap;
+  int32_t* c0_tiles;   // [B+1] prefix sum of the 128-frame conv0 tiles of every utterance (conv0_tc_kernel)
   double2* gn_partial; float2* gn_affine; int gn_tiles;
   bf16 *cbuf0, *cbuf1; bf16* featln; bf16* posin;
   StackBufs sb; float* acc;
@@ -1473,6 +1476,7 @@ void carve_w2v(const serenc_handle* h, const W2VPlan& p, void* base, W2VWs* w) {
   w->stats = cv.take<float2>(p.batch);
   w->foff = cv.take<int32_t>(p.batch + 1);
   w->r6 = cv.take<int32_t>(p.batch);
+  w->c0_tiles = cv.take<int32_t>(p.batch + 1);
   w->fp_gather = cv.take<int32_t>(p.sumT);
   w->gap_row = cv.take<int32_t>(p.sumT);
   w->pos_rowmap = cv.take<int32_t>(p.mpos);
@@ -1636,10 +1640,11 @@ static int encode_w2v_impl(serenc_handle* h, const serenc_w2v_call& a) {
   if (frame_offsets_out) for (int b = 0; b <= batch; ++b) frame_offsets_out[b] = p.foff[b];
 
   // ---- per-utterance tables -> device ----
+  int c0_total_tiles = 0;
   {
     const size_t sz_u = sizeof(Conv0Utt) * batch, sz_f = 4 * (size_t)(batch + 1), sz_r = 4 * (size_t)batch;
     void* hs;
-    SERENC_TRY(stage_reserve(sz_u + sz_f + sz_r + 64, &hs, st));
+    SERENC_TRY(stage_reserve(sz_u + 2 * sz_f + sz_r + 64, &hs, st));
     Conv0Utt* hu = reinterpret_cast<Conv0Utt*>(hs);
     for (int b = 0; b < batch; ++b) {
       hu[b].sample_start = sample_start[b];
@@ -1653,6 +1658,11 @@ static int encode_w2v_impl(serenc_handle* h, const serenc_w2v_call& a) {
     memcpy(hf, p.foff.data(), sz_f);
     int32_t* hr = hf + batch + 1;
     memcpy(hr, p.r6.data(), sz_r);
+    int32_t* ht = hr + batch;
+    ht[0] = 0;
+    for (int b = 0; b < batch; ++b) ht[b + 1] = ht[b] + ceil_div((p.T[6][b] + 2) << 6, C0T_BM);
+    c0_total_tiles = ht[batch];
+    SERENC_CUDA_OK(cudaMemcpyAsync(w.c0_tiles, ht, sz_f, cudaMemcpyHostToDevice, st));
     SERENC_CUDA_OK(cudaMemcpyAsync(w.utts, hu, sz_u, cudaMemcpyHostToDevice, st));
     SERENC_CUDA_OK(cudaMemcpyAsync(w.foff, hf, sz_f, cudaMemcpyHostToDevice, st));
     SERENC_CUDA_OK(cudaMemcpyAsync(w.r6, hr, sz_r, cudaMemcpyHostToDevice, st));
@@ -1680,8 +1690,10 @@ static int encode_w2v_impl(serenc_handle* h, const serenc_w2v_call& a) {
     const float2* stp = normalize ? w.stats : nullptr;
     const float* b0 = c.conv_bias ? h->conv_b[0] : nullptr;
     if (!c.conv_group_norm) {
+      // LayerNorm variant: the 10-tap dot products on the tensor cores, LayerNorm + GELU straight out of TMEM (conv0_tc.cuh)
       ProfScope ps(h, SERENC_PROF_CONV0, 1, 2.0 * t0sum * CONV0_C * CONV0_K, (wav_i16 ? 2.0 : 4.0) * nsamp0 + 2.0 * t0sum * CONV0_C, st);
-      conv0_kernel<0><<<grid, 256, 0, st>>>(wav_dev, wav_i16, w.utts, stp, h->conv0_w, b0, h->conv_g[0], h->conv_be[0], w.cbuf0, nullptr, nullptr, 0);
+      const int ctas = c0_total_tiles < h->num_sms ? c0_total_tiles : h->num_sms;
+      conv0_tc_kernel<<<ctas, C0T_THREADS, C0T_SMEM, st>>>(wav_dev, wav_i16, w.utts, w.c0_tiles, batch, stp, h->conv0_w, b0, h->conv_g[0], h->conv_be[0], w.cbuf0);
       SERENC_CUDA_OK(cudaGetLastError());
     } else {
       // GroupNorm(512 groups) on conv0: statistics over each utterance's valid frames, then recompute + apply

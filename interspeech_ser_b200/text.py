@@ -194,6 +194,16 @@ class RobertaModel(_Base):
     """RobertaModel replacement (HF modeling_roberta.py): embeddings + post-LN encoder; the pooler is not on this path
     (`pooler_output` is None: the reference reads hidden_states / last_hidden_state only)."""
 
+    @classmethod
+    def from_pretrained(cls, name_or_path: str, **kw) -> "RobertaModel":
+        """RobertaModel.from_pretrained(SSL_TYPE) (preprocess_roberta.py:104): same resolution rules as AutoModel."""
+        from .modeling import AutoModel
+
+        model = AutoModel.from_pretrained(name_or_path, **kw)
+        if not isinstance(model, cls):
+            raise OSError(f"'{name_or_path}' is not a RoBERTa checkpoint")
+        return model
+
     def forward(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, token_type_ids=None,
                 position_ids=None, output_hidden_states: Optional[bool] = None, output_attentions: Optional[bool] = None,
                 return_dict: Optional[bool] = None, **kw) -> ModelOutput:

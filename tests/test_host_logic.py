@@ -239,3 +239,64 @@ def test_epilogue_gelu_constants_are_exact_to_roundoff():
     body = body[:body.index("return fmaf(-a, e, hx + a);")]
     consts = [float(v) for v in re.findall(r"(-?\d\.\d{9}e[+-]\d\d)f", body)]
     assert consts == list(reversed(gelu_fit.COEFFS))      # Horner order in the kernel = descending powers
+
+
+def test_request_coalescing_queue_groups_concurrent_calls():
+    """enable_request_batching (SURVEY 8b "Threading"): concurrent single-utterance calls are collected by the dispatcher
+    and handed to ONE engine call per kind; every caller gets its own slice; an exception reaches exactly the callers of
+    the failing group and the dispatcher keeps serving. (Host logic only: a stand-in model records what it is given.)"""
+    import threading
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    from interspeech_ser_b200.modeling import _CoalescingQueue
+
+    class FakeModel:
+        def __init__(self):
+            self.calls = []
+
+        def _run_coalesced(self, kind, items):
+            self.calls.append((kind, len(items)))
+            if any(it[1] == "boom" for it in items):
+                raise ValueError("bad utterance")
+            time.sleep(0.01)
+            return [(kind, it[1]) for it in items]
+
+    m = FakeModel()
+    q = _CoalescingQueue(m, max_batch=8, max_wait_ms=30.0)
+    try:
+        gate = threading.Barrier(4)
+
+        def work(i):
+            gate.wait()
+            return q.submit((i % 2 == 0, f"utt{i}")).result(timeout=10)
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            got = list(ex.map(work, range(4)))
+        assert got == [(True, "utt0"), (False, "utt1"), (True, "utt2"), (False, "utt3")]
+        assert q.requests == 4 and q.batches == 2 and sorted(m.calls) == [(False, 2), (True, 2)]   # one call per kind
+        f_bad, f_ok = q.submit((True, "boom")), q.submit((False, "fine"))
+        with pytest.raises(ValueError):
+            f_bad.result(timeout=10)
+        assert f_ok.result(timeout=10) == (False, "fine")
+        assert q.submit((True, "after")).result(timeout=10) == (True, "after")
+    finally:
+        q.close()
+    with pytest.raises(RuntimeError):
+        q.submit((True, "closed"))
+
+
+def test_int16_wav_decode_is_a_view_and_matches_float_decode(tmp_path):
+    """audio_io keep_int16: mono 16-bit PCM comes back as the int16 samples (the GPU applies 1 / 32768, include/serenc.h
+    SERENC_WAV_I16); scaled on the host it equals the float decode bit for bit; other formats fall back to float32."""
+    from interspeech_ser_b200 import audio_io
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(5000) * 0.2).astype(np.float32)
+    path = str(tmp_path / "a.wav")
+    audio_io.write_wav(path, x)
+    data = audio_io.read_bytes(path)
+    pcm, sr = audio_io.decode_wav(data, path, keep_int16=True)
+    flt, _ = audio_io.decode_wav(data, path)
+    assert pcm.dtype == np.int16 and sr == 16000 and pcm.shape == flt.shape
+    assert np.array_equal(pcm.astype(np.float32) * np.float32(1.0 / 32768.0), flt)
+    y, sr2 = audio_io.load_audio_bytes(data, path, sr=8000, keep_int16=True)       # resampled: float32 again
+    assert y.dtype == np.float32 and sr2 == 8000 and abs(len(y) - 2500) <= 1
