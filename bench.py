@@ -444,6 +444,26 @@ def run_workload(name, args, ctx, model, steps, warmup, headline):
     ms_total, wall, ms_own = timer.timed(step_device, steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # per-kernel-class device time for the roofline: separate, instrumented steps (an event pair around every launch)
+    # run DIRECTLY behind the timed loop, so that they see the same power state / SM clock as the number they explain
+    eng.set_profiling(True)
+    prof_steps = 3 if headline else 1
+    saved = os.environ.get("SERENC_NO_GRAPH")
+    os.environ["SERENC_NO_GRAPH"] = "1"          # per-class events are recorded by the eager path only
+    try:
+        l0 = eng.launch_count()
+        for _ in range(prof_steps):
+            timer.flush.zero_()
+            step_device()
+        launches = (eng.launch_count() - l0) // prof_steps    # kernels per step (launched directly, or replayed from the cached graph)
+        prof = eng.get_profile()
+    finally:
+        eng.set_profiling(False)
+        if saved is None:
+            os.environ.pop("SERENC_NO_GRAPH", None)
+        else:
+            os.environ["SERENC_NO_GRAPH"] = saved
+
     for _ in range(2):
         step_e2e()
     torch.cuda.synchronize()
@@ -492,25 +512,6 @@ def run_workload(name, args, ctx, model, steps, warmup, headline):
             extra = {"gathered_shape": list(mat.shape), "gathered_sha256": hashlib.sha256(mat.numpy().tobytes()).hexdigest(),
                      "per_rank_busy_ms_per_step": [float(b.item()) for b in busy_all],
                      "note": "the sha256 of the gathered, un-permuted [utterances, d] matrix is the same for every world size (bitwise equality with N = 1)"}
-
-    # per-kernel-class device time for the roofline (separate, instrumented steps)
-    eng.set_profiling(True)
-    prof_steps = 2 if headline else 1
-    saved = os.environ.get("SERENC_NO_GRAPH")
-    os.environ["SERENC_NO_GRAPH"] = "1"          # per-class events are recorded by the eager path only
-    try:
-        l0 = eng.launch_count()
-        for _ in range(prof_steps):
-            timer.flush.zero_()
-            step_device()
-        launches = (eng.launch_count() - l0) // prof_steps    # kernels per step (launched directly, or replayed from the cached graph)
-        prof = eng.get_profile()
-    finally:
-        eng.set_profiling(False)
-        if saved is None:
-            os.environ.pop("SERENC_NO_GRAPH", None)
-        else:
-            os.environ["SERENC_NO_GRAPH"] = saved
 
     if rank != 0:
         return None, ok

@@ -195,6 +195,7 @@ conv0_tc_kernel(const void* __restrict__ wav, int wav_i16, const Conv0Utt* __res
     const float* pg = s_par + CONV0_C + half * 256;
     const float* pe = s_par + 2 * CONV0_C + half * 256;
     const int sr = lane >> 2, sc = lane & 3;                   // coalesced phase: row 8 i + lane / 4, 16-byte segment lane % 4
+    const bool has_bias = bias != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int b = find_utt(tile);
@@ -203,23 +204,29 @@ conv0_tc_kernel(const void* __restrict__ wav, int wav_i16, const Conv0Utt* __res
       mbar_wait(bar_full, (uint32_t)(it & 1));
       tc_fence_after();
 
-      // pass 1: half-row statistics about a pivot (this half's first value + bias): stable one-pass variance
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(t_addr, r);
+      // pass 1: half-row statistics about a pivot (this half's first value + bias): stable one-pass variance.
+      // Both passes keep the NEXT 32-column block's tcgen05.ld in flight while the current one is processed.
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32b_x32(t_addr, ra);
       tmem_ld_wait();
-      const float pivot = __uint_as_float(r[0]) + pb[0];
+      tmem_ld_32x32b_x32(t_addr + 32u, rb);
+      const float pivot = __uint_as_float(ra[0]) + pb[0];
       const uint64_t npv2 = pack_f32x2(-pivot, -pivot);
       uint64_t s2 = 0ull, q2 = 0ull;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < 8; ++c) {
+        uint32_t (&r)[32] = (c & 1) ? rb : ra;
         if (c > 0) {
-          tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
           tmem_ld_wait();
+          if (c + 1 < 8) tmem_ld_32x32b_x32(t_addr + (uint32_t)((c + 1) * 32), (c & 1) ? ra : rb);
         }
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-          const float2 bb = *reinterpret_cast<const float2*>(pb + c * 32 + k);
-          const uint64_t d = fadd2(fadd2(pack_f32x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), pack_f32x2(bb.x, bb.y)), npv2);
+          uint64_t d = fadd2(pack_f32x2(__uint_as_float(r[k]), __uint_as_float(r[k + 1])), npv2);
+          if (has_bias) {   // CTA-uniform
+            const float2 bb = *reinterpret_cast<const float2*>(pb + c * 32 + k);
+            d = fadd2(d, pack_f32x2(bb.x, bb.y));
+          }
           s2 = fadd2(s2, d);
           q2 = ffma2(d, d, q2);
         }
@@ -238,6 +245,7 @@ conv0_tc_kernel(const void* __restrict__ wav, int wav_i16, const Conv0Utt* __res
       const float d0 = mu - pivot, d1 = mu - p1;
       const float var = ((qv - 2.f * d0 * sv + 256.f * d0 * d0) + (q1 - 2.f * d1 * s1 + 256.f * d1 * d1)) * (1.f / CONV0_C);
       const float rs = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+      tmem_ld_32x32b_x32(t_addr, ra);   // first block of pass 2, in flight across the barrier
       c0t_pair_barrier(quarter);   // the exchange buffer is free again for the next tile
 
       // pass 2: normalise + affine + GELU -> bf16 -> staging -> 16-byte stores (64 contiguous bytes per row and block)
@@ -249,22 +257,27 @@ conv0_tc_kernel(const void* __restrict__ wav, int wav_i16, const Conv0Utt* __res
         orow[i] = t < u.slot ? u.row0 + t : -1;
         ozero[i] = t >= u.T0;             // slot padding rows: zeros, as every later layer expects finite values there
       }
-      const uint64_t nmu2 = pack_f32x2(-mu, -mu), rs2 = pack_f32x2(rs, rs);
-#pragma unroll 1
+      const float nmurs = -mu * rs;
+      const uint64_t nmurs2 = pack_f32x2(nmurs, nmurs), rs2 = pack_f32x2(rs, rs);   // (x - mu) rs = x rs + (-mu rs): one FFMA2
+#pragma unroll
       for (int c = 0; c < 8; ++c) {
-        tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+        uint32_t (&r)[32] = (c & 1) ? rb : ra;
         tmem_ld_wait();
+        if (c + 1 < 8) tmem_ld_32x32b_x32(t_addr + (uint32_t)((c + 1) * 32), (c & 1) ? ra : rb);
 #pragma unroll
         for (int k8 = 0; k8 < 4; ++k8) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const int col = c * 32 + k8 * 8 + e;
-            const float2 bb = *reinterpret_cast<const float2*>(pb + col);
             const float2 gg = *reinterpret_cast<const float2*>(pg + col);
             const float2 be = *reinterpret_cast<const float2*>(pe + col);
-            uint64_t v = fadd2(fadd2(pack_f32x2(__uint_as_float(r[k8 * 8 + e]), __uint_as_float(r[k8 * 8 + e + 1])), pack_f32x2(bb.x, bb.y)), nmu2);
-            v = ffma2(fmul2(v, rs2), pack_f32x2(gg.x, gg.y), pack_f32x2(be.x, be.y));
+            uint64_t v = pack_f32x2(__uint_as_float(r[k8 * 8 + e]), __uint_as_float(r[k8 * 8 + e + 1]));
+            if (has_bias) {   // CTA-uniform
+              const float2 bb = *reinterpret_cast<const float2*>(pb + col);
+              v = fadd2(v, pack_f32x2(bb.x, bb.y));
+            }
+            v = ffma2(ffma2(v, rs2, nmurs2), pack_f32x2(gg.x, gg.y), pack_f32x2(be.x, be.y));
             float v0, v1;
             unpack_f32x2(v, v0, v1);
             gelu_fast2(v0, v1, v0, v1);

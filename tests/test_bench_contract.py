@@ -33,3 +33,21 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_exit_quietly():
     res = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert res.returncode == 0 and not [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_both_arms_print_the_same_config_and_every_baseline_workload_is_listed():
+    """The reference arm has to run on the B200 arm's `config` (same object for both), and the default line has to carry
+    every BASELINE config as a workload."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in bench.WORKLOADS:
+        a, b = bench.workload_config(name, 1), bench.workload_config(name, 1)
+        assert a == b and a["model"] == bench.WORKLOADS[name]["model"] and "workload" in a
+    assert set(bench.DEFAULT_EXTRAS) == {"whisper-large-v3", "hubert-xlarge", "xls-r-2b", "wavlm-large-c1", "wavlm-large-sweep"}
+    assert bench.WORKLOADS["wavlm-large-corpus"].get("strong") and bench.workload_config("wavlm-large-corpus", 8)["global_batch"] == 4096
+    for name in bench.DEFAULT_EXTRAS:
+        assert bench.WORKLOADS[name]["model"] in bench.GOLDEN      # every benched model has a committed HF golden for the in-bench check
+    for f in bench.GOLDEN.values():
+        assert os.path.isfile(os.path.join(REPO, "tests", "golden", f)), f
