@@ -324,12 +324,15 @@ struct LnGate {
 };
 
 // Rows per warp: narrow rows give a warp too little to do per trip to HBM, so it keeps several rows in flight.
+// (Round 2 re-measured the choice with the RPW_ template parameter below, profiles/r02k_ln_rpw.log: width 512 at 1 / 2 / 4 / 8
+// rows per warp = 457 / 421 / 424 / 637 us for 908 k rows (6.6 TB/s at 2-4, the HBM copy peak), width 1 024 at 1-2 / 4 = 36.9 /
+// 45.1 us for 28 258 rows: the built-in choices stand.)
 template <int NV>
 struct LnRows {
   static constexpr int RPW = NV <= 4 ? 4 : (NV <= 8 ? 2 : 1);
 };
 
-template <int NV, typename TIn, typename TOut, bool GELU>
+template <int NV, typename TIn, typename TOut, bool GELU, int RPW_ = LnRows<NV>::RPW>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restrict__ in, int64_t ld_in,
                                                               TOut* __restrict__ out, int64_t ld_out,
                                                               const float* __restrict__ gamma,
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
   // and the same values feed the next GEMM)
   // gate: optional WavLM gate of the NEXT attention (head_dim 64: the 2 heads of a 128-column chunk are its two
   // half-warps), computed from the fp32 normalised row that is in registers anyway
-  constexpr int RPW = LnRows<NV>::RPW;
+  constexpr int RPW = RPW_;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;

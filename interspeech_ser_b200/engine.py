@@ -61,6 +61,35 @@ class UploadRing:
         self._bufs: List[Optional[torch.Tensor]] = [None] * slots
         self._free: List[Optional[torch.cuda.Event]] = [None] * slots
         self._i = 0
+        # pinned host staging, one buffer per slot, grown on demand and then reused: packing a batch costs a memcpy, not a
+        # cudaHostAlloc per call (round 1 pinned a fresh tensor for every batch)
+        self._hbufs: List[Optional[torch.Tensor]] = [None] * slots
+        self._h2d_done: List[Optional[torch.cuda.Event]] = [None] * slots
+
+    def upload_arrays(self, arrays, dtype: torch.dtype) -> Tuple[torch.Tensor, int]:
+        """Pack numpy arrays back to back into this slot's pinned staging buffer (converted to `dtype`; int16 PCM that has
+        to become float32 is scaled by 1 / 32768 as librosa does) and upload it."""
+        import numpy as np
+        s = self._i % len(self._bufs)
+        n = int(sum(len(a) for a in arrays))
+        es = torch.empty((), dtype=dtype).element_size()
+        hb = self._hbufs[s]
+        if self._h2d_done[s] is not None:
+            self._h2d_done[s].synchronize()      # the previous upload out of this host buffer (two batches ago) has been read
+        if hb is None or hb.numel() < n * es:
+            hb = self._hbufs[s] = torch.empty(max(int(n * es * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
+        host = hb[: n * es].view(dtype)
+        dst = host.numpy()
+        off = 0
+        for a in arrays:
+            m = len(a)
+            if dtype == torch.float32 and getattr(a, "dtype", None) == np.int16:
+                np.multiply(a, np.float32(1.0 / 32768.0), out=dst[off:off + m], dtype=np.float32)
+            else:
+                dst[off:off + m] = a
+            off += m
+        out = self.upload(host)
+        return out
 
     def upload(self, host: torch.Tensor) -> Tuple[torch.Tensor, int]:
         assert host.dtype in (torch.float32, torch.int16, torch.int32) and host.dim() == 1 and not host.is_cuda
@@ -86,6 +115,7 @@ class UploadRing:
             buf[:n].copy_(host, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.copy_stream)
+        self._h2d_done[s] = done
         cur.wait_event(done)
         return buf[:n], s
 

@@ -81,16 +81,6 @@ class Extracted:
     ranges: Optional[List[Tuple[int, int]]] = None   # row range of every utterance inside `packed`
 
 
-def _pack_host(waveforms: Sequence[np.ndarray]) -> torch.Tensor:
-    """Utterances back to back in one pinned host tensor: int16 when every input is int16 PCM, else float32."""
-    if len(waveforms) and all(getattr(w, "dtype", None) == np.int16 for w in waveforms):
-        flat = np.concatenate([np.asarray(w, dtype=np.int16) for w in waveforms])
-    else:
-        flat = np.concatenate([np.asarray(w, dtype=np.float32) if getattr(w, "dtype", None) != np.int16
-                               else np.asarray(w, dtype=np.float32) / np.float32(32768.0) for w in waveforms])
-    return torch.from_numpy(flat).pin_memory()
-
-
 class _Base:
     def __init__(self, cfg: EncoderConfig, tensors: Dict[str, np.ndarray], device=0):
         self.cfg = cfg
@@ -106,6 +96,20 @@ class _Base:
             ring = self._ring_tls.ring = UploadRing(self.device)
         wav, slot = ring.upload(host)
         return ring, wav, slot
+
+    @torch.no_grad()
+    def _extract_arrays(self, waveforms: Sequence[np.ndarray], lens: Sequence[int], **kw) -> "Extracted":
+        """extract() for numpy waveforms: packed straight into the upload ring's reusable pinned staging buffer (int16 when
+        every input is int16 PCM, else float32), uploaded on the copy stream, encoded."""
+        all_i16 = len(waveforms) > 0 and all(getattr(w, "dtype", None) == np.int16 for w in waveforms)
+        with torch.cuda.device(self.device):
+            ring = getattr(self._ring_tls, "ring", None)
+            if ring is None:
+                ring = self._ring_tls.ring = UploadRing(self.device)
+            wav, slot = ring.upload_arrays(waveforms, torch.int16 if all_i16 else torch.float32)
+            res = self.extract_device(wav, lens, **kw)
+            ring.release(slot)
+        return res
 
     @torch.no_grad()
     def extract_pinned(self, host: torch.Tensor, lens: Sequence[int], **kw) -> "Extracted":
@@ -336,8 +340,8 @@ class SpeechEncoderModel(_Base):
         Waveforms may be float32 samples or int16 PCM (all of one kind): int16 halves the upload and is scaled by
         1 / 32768 inside the first kernel, exactly as librosa scales it on the host."""
         lens = [int(len(w)) for w in waveforms]
-        return self.extract_pinned(_pack_host(waveforms), lens, layer=layer, average=average, want_frames=want_frames,
-                                   want_pooled=want_pooled, **kw)
+        return self._extract_arrays(waveforms, lens, layer=layer, average=average, want_frames=want_frames,
+                                    want_pooled=want_pooled, **kw)
 
     @torch.no_grad()
     def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
@@ -414,8 +418,8 @@ class WhisperModel(_Base):
         reproducing the script's `feats.shape[1]`, else 1500). float32 samples or int16 PCM."""
         waveforms = [np.asarray(w)[:480000] for w in waveforms]
         lens = [int(len(w)) for w in waveforms]
-        return self.extract_pinned(_pack_host(waveforms), lens, layer=layer, average=average, want_frames=want_frames,
-                                   want_pooled=want_pooled, literal_crop=literal_crop, **kw)
+        return self._extract_arrays(waveforms, lens, layer=layer, average=average, want_frames=want_frames,
+                                    want_pooled=want_pooled, literal_crop=literal_crop, **kw)
 
     @torch.no_grad()
     def extract_device(self, wav: torch.Tensor, lens: Sequence[int], layer: int = -1, average: bool = False,
