@@ -78,14 +78,22 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
 };
 
+// TMA_NB = 0: epilogue through registers + a transpose staging tile. TMA_NB = 2: fp32 epilogue through TMA with two
+// 32 x 32 fp32 blocks (128-byte rows, 128B swizzle) per epilogue warp in place of the staging. (Three blocks cost an operand
+// stage; measured, r02o: 4 stages + 3 blocks = 779 TFLOP/s on the out-projection shape against 855 for 5 + 2, FC2 shape
+// 1 166 against 1 329 - the operand ring needs its depth.)
+constexpr int GEMM2_RING_BLOCK_BYTES = 32 * 32 * 4;
+template <int TMA_NB>
 struct Gemm2Cfg {
-  static constexpr int STAGES = GEMM2_STAGES;
+  static constexpr int STAGES = TMA_NB == 3 ? GEMM2_STAGES - 1 : GEMM2_STAGES;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // this CTA's 128 rows of A
   static constexpr int B_BYTES = (GEMM2_BN / 2) * GEMM_BK * 2; // this CTA's 128 rows of W
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // 32 KB
   static constexpr int TMEM_COLS = 512;                        // 2 x 256 accumulator columns
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + GEMM_STAGING_BYTES + BAR_BYTES + 1024;
+  static constexpr int EPI_BYTES = TMA_NB ? GEMM_EPI_WARPS * TMA_NB * GEMM2_RING_BLOCK_BYTES : GEMM_STAGING_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16 + GEMM_EPI_WARPS * TMA_NB * 8;   // + one mbarrier per ring block
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;      // +1024: alignment slack
+  static_assert(SMEM_BYTES <= 227 * 1024, "CTA-pair GEMM exceeds the shared memory of an SM");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -419,25 +427,166 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 epilogue of the CTA-pair kernel through TMA (plain Linear into the fp32 residual stream: out-projection, FC2)
+// ------------------------------------------------------------------------------------------------
+// The register-staged path above fetches the residual one 32-column block ahead and its loads sit in front of every block
+// (three buffers would spill: 145 registers already). Here a warp owns NB 4 KB shared-memory blocks: the residual block is
+// bulk-loaded by TMA NB blocks ahead - across tile boundaries, so the first two blocks of a tile arrive under its mainloop -
+// each thread adds its accumulator row to its own 128-byte row of the block in place (row-per-thread is conflict-free under
+// the 128B swizzle: lane l touches 16-byte chunk j ^ (l & 7)), and a TMA store writes the block back: no transpose, no
+// LDG / STG, no per-row address arithmetic; rows past M and columns past N are clipped by the tensor map.
+// A block is (tile, c): rows row0 .. +31 of the warp's lane quarter, columns col0 = n0 + 32 c, c = 0..3; blocks with
+// col0 >= N (N tail of the last tile column) do not exist for either the prefetch or the consumer.
+template <int BN, int NB>
+__device__ __forceinline__ void gemm2_epilogue_tma(const GemmParams& p, const CUtensorMap* tmR, const CUtensorMap* tmO,
+                                                   uint8_t* ring, uint64_t* rfull, uint32_t tmem_base, int ew, int half,
+                                                   int rank, int pair, int num_pairs, int num_tiles, int lane,
+                                                   uint64_t* tfull_bar, uint64_t* tempty_bar) {
+  constexpr int RB = GEMM2_RING_BLOCK_BYTES;
+  const bool has_res = p.resid != nullptr;
+  auto coords = [&](int tile, int c, int& row0, int& col0) {
+    const TileCoord tc = decode_tile(p, tile);
+    row0 = tc.m_t * (2 * GEMM_BM) + rank * GEMM_BM + ew * 32;
+    col0 = tc.n_t * BN + half * (BN / 2) + c * 32;
+  };
+  // prefetch cursor over the existing blocks of this warp
+  int pt = pair, pc = -1;
+  auto advance = [&]() {
+    for (;;) {
+      if (++pc == 4) {
+        pc = 0;
+        pt += num_pairs;
+      }
+      if (pt >= num_tiles) return;
+      int r0, c0;
+      coords(pt, pc, r0, c0);
+      if (c0 < p.n_per_group) return;
+    }
+  };
+  int ibuf = 0;   // ring slot of the next block to load
+  auto issue_load = [&]() {   // whole warp
+    if (pt < num_tiles) {
+      if (has_res) {
+        int r0, c0;
+        coords(pt, pc, r0, c0);
+        uint64_t* bar = &rfull[ibuf];
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(bar, RB);
+          tma_load_2d(ring + ibuf * RB, tmR, bar, c0, r0);
+        }
+        __syncwarp();
+      }
+      if (++ibuf == NB) ibuf = 0;
+      advance();
+    }
+  };
+  if (pair < num_tiles) advance();
+#pragma unroll
+  for (int i = 0; i < NB; ++i) issue_load();
+
+  int dbuf = 0;          // ring slot of the block being consumed
+  uint32_t dphase = 0;   // its mbarrier parity
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  int it = 0;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+    const bool tracing = p.trace && blockIdx.x == 0 && threadIdx.x == 0;
+    if (tracing) p.trace[it * 8 + 4] = clock64();
+    const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
+    if (tracing) p.trace[it * 8 + 5] = clock64();
+    bool released = false;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      int row0, col0;
+      coords(tile, c, row0, col0);
+      if (col0 >= p.n_per_group) break;   // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(t_addr + (uint32_t)(c * 32), r);
+      if (has_res) mbar_wait(&rfull[dbuf], dphase);
+      uint8_t* blk = ring + dbuf * RB;
+      uint8_t* row = blk + lane * 128;
+      tmem_ld_wait();
+      if (c == 3 || col0 + 32 >= p.n_per_group) {   // the tile's last block is in registers: hand the accumulator back now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
+        released = true;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4* slot = reinterpret_cast<float4*>(row + (((uint32_t)j ^ sw) << 4));
+        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+        if (p.bias) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+          unpack_f32x2(fadd2(pack_f32x2(v.x, v.y), pack_f32x2(bv.x, bv.y)), v.x, v.y);
+          unpack_f32x2(fadd2(pack_f32x2(v.z, v.w), pack_f32x2(bv.z, bv.w)), v.z, v.w);
+        }
+        if (p.act == 1) {
+          gelu_fast2(v.x, v.y, v.x, v.y);
+          gelu_fast2(v.z, v.w, v.z, v.w);
+        }
+        if (has_res) {
+          const float4 q = *slot;
+          unpack_f32x2(fadd2(pack_f32x2(v.x, v.y), pack_f32x2(q.x, q.y)), v.x, v.y);
+          unpack_f32x2(fadd2(pack_f32x2(v.z, v.w), pack_f32x2(q.z, q.w)), v.z, v.w);
+        }
+        *slot = v;
+      }
+      fence_proxy_async_smem();   // generic-proxy writes of the block -> visible to the TMA store
+      __syncwarp();
+      if (elect_one_sync()) {
+        tma_store_2d(tmO, blk, col0, row0);
+        bulk_commit_group();
+        bulk_wait_read_all();     // the slot is refilled right away (ibuf == dbuf here: NB loads are always outstanding)
+      }
+      __syncwarp();
+      if (++dbuf == NB) {
+        dbuf = 0;
+        dphase ^= 1u;
+      }
+      issue_load();
+    }
+    if (!released) {   // a warp whose column half lies past N in this tile column
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+    }
+    if (tracing) p.trace[it * 8 + 6] = clock64();
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // CTA-pair kernel: 256 x 256 tiles, tcgen05.mma.cta_group::2
 // ------------------------------------------------------------------------------------------------
-template <bool EPI_BF16>
+// EPI_BF16: bf16-only outputs. TMA_NB > 0 (fp32 outputs only): the epilogue moves the residual / output blocks with TMA
+// (gemm2_epilogue_tma; tmR / tmO are fp32 maps with 32 x 32 boxes, tmR unused without a residual).
+template <bool EPI_BF16, int TMA_NB = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                              const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = Gemm2Cfg;
+                              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
+                              const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+  static_assert(!(EPI_BF16 && TMA_NB), "the TMA epilogue is the fp32 one");
+  constexpr bool EPI_TMA = TMA_NB > 0;
+  using Cfg = Gemm2Cfg<TMA_NB>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = GEMM2_BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + GEMM_STAGING_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);   // EPI_TMA: the block ring (1 024-aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  [[maybe_unused]] uint64_t* ring_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // EPI_TMA: [8 warps][TMA_NB blocks]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -449,6 +598,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    if constexpr (EPI_TMA) {
+      tma_prefetch_desc(&tmR);
+      tma_prefetch_desc(&tmO);
+    }
   }
   if (warp == GEMM_WARP_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -458,6 +611,9 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);                    // multicast tcgen05.commit from the leader
       mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);  // every epilogue warp of both CTAs (used in the leader only)
+    }
+    if constexpr (EPI_TMA) {
+      for (int i = 0; i < TMA_NB * GEMM_EPI_WARPS; ++i) mbar_init(&ring_bar[i], 1);
     }
     fence_mbar_init();
   }
@@ -553,6 +709,11 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
     // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
     const int ew = warp & 3;
     const int half = warp >> 2;
+    if constexpr (EPI_TMA) {
+      gemm2_epilogue_tma<BN, TMA_NB>(p, &tmR, &tmO, reinterpret_cast<uint8_t*>(staging) + warp * (TMA_NB * GEMM2_RING_BLOCK_BYTES),
+                             ring_bar + TMA_NB * warp, tmem_base, ew, half, (int)rank, pair, num_pairs, num_tiles, lane, tfull_bar,
+                             tempty_bar);
+    } else {
     float* st = staging + warp * (32 * GEMM_ST_LD);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -570,6 +731,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));  // leader's barrier
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
     }
   }
 

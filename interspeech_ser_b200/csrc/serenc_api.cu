@@ -128,6 +128,7 @@ struct serenc_handle {
   long long* gemm_trace = nullptr;  // debug: device buffer for per-tile clock stamps of the CTA-pair GEMM (serenc_debug_gemm_trace)
   // A/B switches: constant false in the production build; read from the environment only with -DSERENC_AB_ARMS
   bool force_1cta = false;        // bypass the CTA-pair GEMM
+  bool gemm_no_tma_epilogue = false;  // fp32 epilogue of the CTA-pair GEMM through registers (the round-1 path)
   bool no_posconv_slab = false;   // positional conv through the generic implicit GEMM
   bool force_mma_sync_attn = false;  // attention on the mma.sync kernel
   int attn_deep64 = 0;               // bias-free head_dim-64 attention on the deep-pipelined kernel
@@ -282,6 +283,36 @@ int get_tmap(serenc_handle* h, const void* base, uint64_t cols, uint64_t rows, u
   return 0;
 }
 
+// rank-2 fp32 map for the TMA epilogue of the CTA-pair GEMM: dims {cols, rows}, box {32, 32} (128-byte rows), 128B swizzle
+int get_tmap_f32(serenc_handle* h, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, CUtensorMap* out) {
+  std::array<uint64_t, 8> key = {reinterpret_cast<uint64_t>(base), cols, rows, row_stride_bytes, 32, 0, 0, 4};
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    auto it = h->tmaps.find(key);
+    if (it != h->tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (rows == 0) rows = 1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    SERENC_FAIL(SERENC_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (%d): base=%p cols=%llu rows=%llu stride=%llu", (int)r, base,
+                (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->tmaps.size() > 4096) h->tmaps.clear();
+  h->tmaps[key] = *out;
+  return 0;
+}
+
 // rank-3 bf16 map over a packed [rows, 3 * heads * hd] q|k|v buffer seen as {hd, 3 * heads, rows}: box {64, 1, box_rows},
 // 128B swizzle. A box that starts at column 64 of a head runs past the head's extent and is zero-filled there.
 int get_tmap_heads(serenc_handle* h, const void* base, uint64_t hd, uint64_t slots, uint64_t rows, uint64_t row_stride_bytes,
@@ -400,7 +431,7 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
 
 // CTA-pair kernel: 256 x 256 tiles, launched as clusters of 2
 int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<0>;
   GemmParams p;
   p.M = c.M;
   p.n_per_group = c.n_per_group;
@@ -455,10 +486,22 @@ int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const bool epi_bf16 = c.out_bf16 && !c.out_f32 && !c.resid;
-  if (epi_bf16)
-    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<true>, tA0, tA1, tB, p));
-  else
-    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<false>, tA0, tA1, tB, p));
+  // plain Linear into the fp32 stream (out-projection, FC2): residual / output blocks move by TMA
+  const bool epi_tma = !epi_bf16 && c.out_f32 && !c.out_bf16 && !c.rowmap && c.groups == 1 && c.n_per_group % 32 == 0 &&
+                       c.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(c.out_f32) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(c.resid) & 15) == 0 && !h->gemm_no_tma_epilogue;
+  if (epi_bf16) {
+    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<true, 0>, tA0, tA1, tB, tB, tB, p));
+  } else if (epi_tma) {
+    CUtensorMap tR, tO;
+    SERENC_TRY(get_tmap_f32(h, c.out_f32, (uint64_t)c.n_per_group, (uint64_t)c.M, (uint64_t)c.ld_f32 * 4, &tO));
+    if (c.resid) SERENC_TRY(get_tmap_f32(h, c.resid, (uint64_t)c.n_per_group, (uint64_t)c.M, (uint64_t)c.ld_f32 * 4, &tR));
+    else tR = tO;
+    cfg.dynamicSmemBytes = Gemm2Cfg<2>::SMEM_BYTES;
+    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<false, 2>, tA0, tA1, tB, tR, tO, p));
+  } else {
+    SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_2cta_kernel<false, 0>, tA0, tA1, tB, tB, tB, p));
+  }
   return 0;
 }
 
@@ -900,6 +943,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->head_dim = hd;
 #ifdef SERENC_AB_ARMS
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_GEMM_NO_TMA_EPI"); h->gemm_no_tma_epilogue = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_DEEP64"); if (e) h->attn_deep64 = e[0] == '1'; }
@@ -963,8 +1007,9 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<64>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
     attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES));
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
-    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<0>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<0>::SMEM_BYTES));
+    attr(cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg<2>::SMEM_BYTES));
 #ifdef SERENC_AB_ARMS
     if (!st) st = hd == 64 ? set_attn_attr<64>() : (hd == 80 ? set_attn_attr<80>() : set_attn_attr<120>());
 #endif

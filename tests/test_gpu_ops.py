@@ -62,6 +62,37 @@ def test_gemm_epilogues(ctx, M, N, K):
     assert rel_err(out, base + bias + resid) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(3000, 1056, 256), (10240, 1024, 128), (2561, 2048, 320)])
+def test_gemm_fp32_tma_epilogue_variants(ctx, M, N, K):
+    """The CTA-pair GEMM's fp32 epilogue moves residual and output blocks by TMA: row tail (M not a multiple of 256 / 32),
+    column tail (N = 1056: the last tile column holds one 32-column block), residual out of place, GELU before the
+    residual add, no bias; rows past M and the untouched source stay as they were."""
+    cfg, w, eng, lib, dev = ctx
+    g = torch.Generator().manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, generator=g) * 0.5).to(dev)
+    wt = bf(torch.randn(N, K, generator=g) * 0.05).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.1).to(dev)
+    resid = torch.randn(M, N, generator=g).to(dev)
+    base = a.float() @ wt.float().t()
+    # residual out of place, one guard row behind the output
+    out = torch.full((M + 1, N), 7.0, device=dev)
+    keep = resid.clone()
+    _lib.check(lib.serenc_op_gemm(eng._h, a.data_ptr(), M, K, K, wt.data_ptr(), N, bias.data_ptr(), resid.data_ptr(), 0, out.data_ptr(), None, stream(dev)))
+    torch.cuda.synchronize()
+    assert rel_err(out[:M], base + bias + resid) < 1e-4
+    assert torch.equal(resid, keep) and bool((out[M] == 7.0).all())
+    # GELU, then the residual, in place, no bias
+    out2 = resid.clone()
+    _lib.check(lib.serenc_op_gemm(eng._h, a.data_ptr(), M, K, K, wt.data_ptr(), N, None, out2.data_ptr(), 1, out2.data_ptr(), None, stream(dev)))
+    torch.cuda.synchronize()
+    assert rel_err(out2, torch.nn.functional.gelu(base) + resid) < 1e-3   # tanh-form GELU with MUFU.TANH (2^-11 relative)
+    # bias only (no residual: nothing is loaded, the block is built in shared memory and stored)
+    out3 = torch.full((M, N), float("nan"), device=dev)
+    _lib.check(lib.serenc_op_gemm(eng._h, a.data_ptr(), M, K, K, wt.data_ptr(), N, bias.data_ptr(), None, 0, out3.data_ptr(), None, stream(dev)))
+    torch.cuda.synchronize()
+    assert rel_err(out3, base + bias) < 1e-4
+
+
 @pytest.mark.parametrize("rows_in,C,N,taps,s", [(1000, 512, 512, 3, 2), (1001, 512, 512, 2, 2), (777, 128, 256, 3, 1),
                                                  (3002, 1280, 1280, 3, 2), (4100, 512, 512, 3, 2), (40001, 512, 512, 3, 2),
                                                  (40000, 512, 512, 2, 2), (96064, 128, 1280, 3, 1)])

@@ -11,8 +11,11 @@ cfg = configs.get_config("tiny/wavlm")
 eng = Engine(cfg, random_init(cfg, 0), 0)
 lib = _lib.load_library()
 st = torch.cuda.current_stream(dev).cuda_stream
-M, N = 28416, 3072
-for K, mode in ((256, "none"), (1024, "none"), (1024, "bf16"), (1024, "gelu"), (1024, "resid")):
+M, N = 28416, int(os.environ.get("TRACE_N", "3072"))
+CASES = ((256, "none"), (1024, "none"), (1024, "bf16"), (1024, "gelu"), (1024, "resid"))
+if os.environ.get("TRACE_RESID_ONLY") == "1":
+    CASES = ((1024, "bf16"), (1024, "resid"))
+for K, mode in CASES:
     a = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)
     w = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device=dev)
