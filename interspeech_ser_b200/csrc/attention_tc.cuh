@@ -148,6 +148,8 @@ wavlm_gate_kernel(const bf16* __restrict__ hln, int64_t rows, int d, int heads, 
 template <bool WAVLM, int POLY = 0, bool CTLHINT = false>
 __global__ void __launch_bounds__(FA_THREADS, 4)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  pdl_wait();      // launched with programmatic stream serialization (common.cuh): q|k|v come from the kernel before
+  pdl_trigger();
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = align_smem_1024(fa_smem_raw);
   uint8_t* sQ = smem;

@@ -65,6 +65,8 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 template <int HD, bool CTLHINT = false>
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  pdl_wait();      // launched with programmatic stream serialization (common.cuh): q|k|v come from the kernel before
+  pdl_trigger();
   using C = FawCfg<HD>;
   extern __shared__ uint8_t fa_smem_raw[];
   uint8_t* smem = align_smem_1024(fa_smem_raw);

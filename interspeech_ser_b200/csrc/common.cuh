@@ -284,6 +284,17 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch. The kernels of the layer loop (LayerNorm, GEMMs, attention) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the grid is scheduled while the tail of the previous kernel of the
+// stream is still running, sets up (barriers, TMEM, tensor-map prefetch) and then waits here until the previous grid has
+// completed and its writes are visible. Nothing produced or overwritten by an earlier kernel is touched before pdl_wait().
+// pdl_trigger() lets the NEXT kernel of the stream be scheduled once every CTA of this grid has got this far (or has exited);
+// it always follows this kernel's own wait, so a third kernel never overtakes two. Both are no-ops in a plain launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads, completion on an mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const TIn* __restri
   constexpr int RPW = RPW_;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  pdl_wait();
+  pdl_trigger();
   if (row0 >= rows) return;
   // gate constants first: their (L2) latency must overlap the row loads, not follow the statistics
   float4 gwa = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gwa;

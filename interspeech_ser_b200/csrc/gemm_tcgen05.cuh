@@ -324,6 +324,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; A, the residual and the output are touched below
+  pdl_trigger();
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;
 
@@ -625,6 +627,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA0, const __
   cluster_sync_all();   // peer barriers initialised + both allocations done before any cross-CTA traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; A, the residual and the output are touched below
+  pdl_trigger();
 
   const int num_tiles = p.tiles_m * p.tiles_n * p.groups;   // tiles_m counts 256-row tiles here
 

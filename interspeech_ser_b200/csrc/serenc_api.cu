@@ -128,6 +128,7 @@ struct serenc_handle {
   long long* gemm_trace = nullptr;  // debug: device buffer for per-tile clock stamps of the CTA-pair GEMM (serenc_debug_gemm_trace)
   // A/B switches: constant false in the production build; read from the environment only with -DSERENC_AB_ARMS
   bool force_1cta = false;        // bypass the CTA-pair GEMM
+  bool pdl = true;                // programmatic dependent launch for the layer-loop kernels (launch_k)
   bool gemm_no_tma_epilogue = false;  // fp32 epilogue of the CTA-pair GEMM through registers (the round-1 path)
   bool no_posconv_slab = false;   // positional conv through the generic implicit GEMM
   bool force_mma_sync_attn = false;  // attention on the mma.sync kernel
@@ -347,6 +348,27 @@ int get_tmap_heads(serenc_handle* h, const void* base, uint64_t hd, uint64_t slo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Launch with programmatic stream serialization (common.cuh, pdl_wait): ONLY for kernels that execute pdl_wait() before
+// they touch anything an earlier kernel of the stream wrote or still reads - LayerNorm, the GEMMs, the attention kernels.
+// Every other kernel is a plain launch, which waits for all of them to complete.
+// ---------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+int launch_k(serenc_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->pdl ? 1 : 0;
+  SERENC_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------
 struct GemmCall {
@@ -422,10 +444,9 @@ int launch_gemm_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   ProfScope ps(h, c.prof_cls, 1, flops, bytes, st);
   const bool epi_bf16 = c.out_bf16 && !c.out_f32 && !c.resid;
   if (epi_bf16)
-    gemm_bf16_tcgen05_kernel<BN, true><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
+    SERENC_TRY(launch_k(h, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tA0, tA1, tB, p));
   else
-    gemm_bf16_tcgen05_kernel<BN, false><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(tA0, tA1, tB, p);
-  SERENC_CUDA_OK(cudaGetLastError());
+    SERENC_TRY(launch_k(h, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, tA0, tA1, tB, p));
   return 0;
 }
 
@@ -478,13 +499,15 @@ int launch_gemm_2cta(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see launch_k
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = h->pdl ? 2 : 1;
   const bool epi_bf16 = c.out_bf16 && !c.out_f32 && !c.resid;
   // plain Linear into the fp32 stream (out-projection, FC2): residual / output blocks move by TMA
   const bool epi_tma = !epi_bf16 && c.out_f32 && !c.out_bf16 && !c.rowmap && c.groups == 1 && c.n_per_group % 32 == 0 &&
@@ -592,8 +615,8 @@ int launch_ln_t(serenc_handle* h, const TIn* in, int64_t ld_in, TOut* out, int64
   ProfScope ps(h, SERENC_PROF_LAYERNORM, 1, 0.0, (double)rows * cols * (sizeof(TIn) + sizeof(TOut)), st);
 #define SERENC_LN_CASE(NV)                                                                                         \
   case NV:                                                                                                         \
-    layernorm_rows_kernel<NV, TIn, TOut, GELU><<<dim3((unsigned)ceil_div64(rows, 8 * LnRows<NV>::RPW)), block, 0, st>>>( \
-        in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps, out2, (int64_t)cols, gate);                     \
+    SERENC_TRY(launch_k(h, layernorm_rows_kernel<NV, TIn, TOut, GELU>, dim3((unsigned)ceil_div64(rows, 8 * LnRows<NV>::RPW)), \
+                        block, 0, st, in, ld_in, out, ld_out, g, b, rows, in_map, out_map, eps, out2, (int64_t)cols, gate)); \
     break;
   switch (nv) {
     SERENC_LN_CASE(1)
@@ -727,8 +750,8 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
         break;
 #endif
       default:
-        if (wavlm) attention_tc_kernel<true><<<grid, block, smem, st>>>(tmq, tmkv, pt);
-        else attention_tc_kernel<false><<<grid, block, smem, st>>>(tmq, tmkv, pt);
+        if (wavlm) SERENC_TRY(launch_k(h, attention_tc_kernel<true>, grid, block, smem, st, tmq, tmkv, pt));
+        else SERENC_TRY(launch_k(h, attention_tc_kernel<false>, grid, block, smem, st, tmq, tmkv, pt));
     }
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
@@ -748,11 +771,11 @@ int launch_attn(serenc_handle* h, const AttnParams& p, bool wavlm, int tmax, int
     }
 #endif
     if (h->head_dim == 80)
-      attention_tc_wide_kernel<80><<<grid, block, FawCfg<80>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      SERENC_TRY(launch_k(h, attention_tc_wide_kernel<80>, grid, block, FawCfg<80>::SMEM_BYTES, st, tmq, tmkv, pt));
     else if (h->head_dim == 64)
-      attention_tc_wide_kernel<64><<<grid, block, FawCfg<64>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      SERENC_TRY(launch_k(h, attention_tc_wide_kernel<64>, grid, block, FawCfg<64>::SMEM_BYTES, st, tmq, tmkv, pt));
     else
-      attention_tc_wide_kernel<120><<<grid, block, FawCfg<120>::SMEM_BYTES, st>>>(tmq, tmkv, pt);
+      SERENC_TRY(launch_k(h, attention_tc_wide_kernel<120>, grid, block, FawCfg<120>::SMEM_BYTES, st, tmq, tmkv, pt));
     SERENC_CUDA_OK(cudaGetLastError());
     return 0;
   }
@@ -943,6 +966,7 @@ extern "C" int serenc_create(const serenc_config* cfg, int device, serenc_handle
   h->head_dim = hd;
 #ifdef SERENC_AB_ARMS
   { const char* e = getenv("SERENC_FORCE_1CTA"); h->force_1cta = e && e[0] == '1'; }
+  { const char* e = getenv("SERENC_NO_PDL"); h->pdl = !(e && e[0] == '1'); }
   { const char* e = getenv("SERENC_GEMM_NO_TMA_EPI"); h->gemm_no_tma_epilogue = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_NO_POSCONV_SLAB"); h->no_posconv_slab = e && e[0] == '1'; }
   { const char* e = getenv("SERENC_ATTN_MMA_SYNC"); h->force_mma_sync_attn = e && e[0] == '1'; }
