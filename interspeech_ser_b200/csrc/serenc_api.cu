@@ -1579,7 +1579,11 @@ struct Staging {
   cudaEvent_t ev = nullptr;
   bool pending = false;
 };
-thread_local Staging g_stage;
+// one per (thread, device): the event belongs to the device that was current when it was created, and a thread may drive
+// replicas on several devices (tests/test_gpu_round2.py::test_second_replica_on_another_device)
+constexpr int SERENC_MAX_DEVICES = 64;
+thread_local Staging g_stages[SERENC_MAX_DEVICES];
+thread_local int g_stage_dev = 0;   // device of the reservation in flight (stage_reserve .. stage_commit)
 
 // `st` is the stream the staged bytes will be copied on. While that stream is being CAPTURED into a CUDA graph the
 // shared staging buffer must not be used: the copy node re-reads its host source at every replay, and the event
@@ -1602,7 +1606,11 @@ int stage_reserve(size_t bytes, void** out, cudaStream_t st) {
     *out = p;
     return 0;
   }
-  Staging& s = g_stage;
+  int dev = 0;
+  SERENC_CUDA_OK(cudaGetDevice(&dev));   // the entry point made the handle's device current (check_ready)
+  if (dev < 0 || dev >= SERENC_MAX_DEVICES) SERENC_FAIL(SERENC_ERR_INVALID, "device index %d out of range", dev);
+  g_stage_dev = dev;
+  Staging& s = g_stages[dev];
   if (s.pending) { SERENC_CUDA_OK(cudaEventSynchronize(s.ev)); s.pending = false; }
   if (bytes > s.cap) {
     if (s.host) cudaFreeHost(s.host);
@@ -1617,8 +1625,8 @@ int stage_reserve(size_t bytes, void** out, cudaStream_t st) {
 }
 int stage_commit(cudaStream_t st) {
   if (g_stage_captured) return 0;
-  SERENC_CUDA_OK(cudaEventRecord(g_stage.ev, st));
-  g_stage.pending = true;
+  SERENC_CUDA_OK(cudaEventRecord(g_stages[g_stage_dev].ev, st));
+  g_stages[g_stage_dev].pending = true;
   return 0;
 }
 

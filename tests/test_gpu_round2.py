@@ -121,6 +121,32 @@ def test_benched_wavlm_batch_142_rows_equal_batch_1():
     check_embedding(big2[5], torch.from_numpy(g[f"meanlast4_pooled_{j4}"]), "golden utterance inside the 142-batch")
 
 
+def test_back_to_back_calls_are_bit_identical():
+    """The layer-loop kernels are launched with programmatic stream serialization (each sets up under the previous
+    kernel's tail and waits before it touches data): twelve encodes of one ragged batch queued without any host
+    synchronisation, interleaved with a differently-shaped batch that reuses the same workspace, give the same bits
+    every time - for the eager path and for the graph replay of a small batch."""
+    cfg, w, model = get_model("microsoft/wavlm-large")
+    lens = [64000, 31999, 48000, 16000, 64000, 400, 40001, 64000] * 6
+    waves = [synth_wave(9100 + j, n) for j, n in enumerate(lens)]
+    flat = torch.from_numpy(np.concatenate(waves)).cuda()
+    other = torch.from_numpy(np.concatenate([synth_wave(9300 + j, 24000) for j in range(20)])).cuda()
+    outs = []
+    for it in range(12):
+        outs.append(model.extract_device(flat, lens, average=True, want_frames=False, want_pooled=True, use_graph=False).pooled.clone())
+        if it % 3 == 1:
+            model.extract_device(other, [24000] * 20, average=True, want_frames=False, want_pooled=True, use_graph=False)
+    torch.cuda.synchronize()
+    for it in range(1, 12):
+        assert torch.equal(outs[it], outs[0]), it
+    small = torch.from_numpy(np.concatenate(waves[:8])).cuda()
+    ref = model.extract_device(small, lens[:8], average=True, use_graph=False).pooled.clone()
+    reps = [model.extract_device(small, lens[:8], average=True, use_graph=True).pooled.clone() for _ in range(12)]
+    torch.cuda.synchronize()
+    for r in reps:
+        assert torch.equal(r, ref)
+
+
 def test_benched_whisper_batch_32_rows_equal_batch_1():
     """BASELINE configs[1]: Whisper-large-v3, 32 x 30 s. Rows 0 / 17 / 31 of the batch == the window encoded alone."""
     name = "openai/whisper-large-v3"
