@@ -31,6 +31,9 @@
 // shape tcgen05.ld offers) for its half of the tile's columns, transposes each 32x32 block through a padded
 // shared-memory tile and then touches global memory with lanes running along a row: bias / GELU / residual /
 // stores are all 128-byte-coalesced (the row-per-thread layout would cost 32 sectors per request).
+// The CTA-pair kernel's fp32 output (the residual stream of out-projection / FC2) takes a second route: residual blocks
+// in and result blocks out by TMA through swizzled shared memory, no transpose (gemm2_epilogue_tma).
+// Both kernels are launched with programmatic stream serialization: set-up first, pdl_wait() before the first operand.
 #pragma once
 #include "common.cuh"
 
