@@ -14,7 +14,10 @@
 //   * only the weights stream: one [BN x 64] K-block per (tap, channel block) through a TMA ring, each used for BOTH
 //     128-row halves (two accumulators in TMEM), so W traffic per output row is halved as well;
 //   * accumulators are double-buffered in TMEM (2 x 2 x BN columns); the fused epilogue (bias + exact GELU + fp32
-//     residual add, gap-layout -> packed row map) is the generic one.
+//     residual add, gap-layout -> packed row map) is the generic one;
+//   * groups narrower than their padding (HuBERT-xlarge: 80 channels in a 128-channel panel pair, 80 outputs in a 128-column
+//     tile) issue only the K = 16 steps that hold real channels (5 of 8 per tap) and N = 80 MMAs: the kernel is bound by the
+//     MMA issue rate at these narrow shapes, so the zero work was 2x of its time.
 #pragma once
 #include "gemm_tcgen05.cuh"
 
@@ -26,6 +29,9 @@ struct PosConvCfg {
   int taps, kpt;        // taps; 64-channel panels per tap (cg_pad / 64)
   int slab_rows;        // 256 + taps - 1, rounded up to a multiple of 128 (TMA boxes of 128 rows)
   int slab_bufs;        // 1 or 2
+  int cg;               // input channels per group that are not padding (80 of 128 for HuBERT-xlarge): the K = 16 steps of a
+                        // panel that hold only zero padding are not issued
+  int n_mma;            // output columns per MMA: n_per_group rounded up to 16 (80 instead of the 128-column tile)
 };
 
 template <int BN>
@@ -130,7 +136,7 @@ posconv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == GEMM_WARP_MMA) {
     // ------------------------------ MMA issuer (whole warp, one elected lane issues) ------------------------------
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, cfg.n_mma);
       const uint32_t tmem_u = warp_uniform(tmem_base);
       int stage = 0;
       uint32_t phase = 0, n = 0;
@@ -153,13 +159,14 @@ posconv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             // rows [128 hf + t, 128 hf + t + 128) of the slab panel: a row-shifted view
             const uint64_t adesc0 = umma_desc_sw128(slab_addr + (uint32_t)(cc * panel_bytes + t * 128));
             const uint64_t adesc1 = umma_desc_sw128(slab_addr + (uint32_t)(cc * panel_bytes + (GEMM_BM + t) * 128));
+            const int ks = min(GEMM_BK / 16, (cfg.cg - cc * GEMM_BK + 15) / 16);   // K steps of this panel with real channels (>= 1)
             if (elect_one_sync()) {
 #pragma unroll
               for (int k = 0; k < GEMM_BK / 16; ++k)
-                umma_bf16_ss(d_tmem, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                if (k < ks) umma_bf16_ss(d_tmem, adesc0 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
 #pragma unroll
               for (int k = 0; k < GEMM_BK / 16; ++k)
-                umma_bf16_ss(d_tmem + (uint32_t)BN, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                if (k < ks) umma_bf16_ss(d_tmem + (uint32_t)BN, adesc1 + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
               umma_commit(&w_empty[stage]);
             }
             __syncwarp();

@@ -380,6 +380,7 @@ struct GemmCall {
   int a_kpt = 0;              // K-blocks per tap
   int taps = 1;
   int a_group_stride = 0;
+  int a_cg_valid = 0;         // grouped conv: input channels per group that are not padding (0: all a_kpt * 64)
   int64_t M = 0;              // output rows
   const bf16* W = nullptr;    // [w_rows, w_k], K index = tap * (a_kpt*64) + channel
   int64_t w_rows = 0;
@@ -537,6 +538,9 @@ int launch_posconv_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   cfg.kpt = c.a_kpt;
   cfg.slab_rows = ((PC_BM + c.taps - 1 + 127) / 128) * 128;
   cfg.slab_bufs = 2;
+  cfg.cg = (c.a_cg_valid > 0 && c.a_cg_valid <= c.a_kpt * GEMM_BK) ? c.a_cg_valid : c.a_kpt * GEMM_BK;
+  cfg.n_mma = (c.n_per_group + 15) / 16 * 16;
+  if (cfg.n_mma > BN) cfg.n_mma = BN;
   if (S::bytes(cfg) > (size_t)h->max_smem) cfg.slab_bufs = 1;
   if (S::bytes(cfg) > (size_t)h->max_smem) return -1000;   // caller falls back to the generic implicit GEMM
   GemmParams p;
@@ -1829,7 +1833,7 @@ static int encode_w2v_impl(serenc_handle* h, const serenc_w2v_call& a) {
     }
     GemmCall g;
     g.A = w.posin; g.a_cols = ld_pos; g.a_rows = p.rgap; g.a_ld = ld_pos; g.a_stride = 1; g.a_kpt = h->pos_cg_pad / GEMM_BK;
-    g.taps = c.pos_conv_kernel; g.a_group_stride = h->pos_cg_pad;
+    g.taps = c.pos_conv_kernel; g.a_group_stride = h->pos_cg_pad; g.a_cg_valid = h->pos_cg;
     g.M = p.mpos; g.W = h->pos_w; g.w_rows = d; g.n_per_group = h->pos_cg; g.groups = c.pos_conv_groups;
     g.bias = h->pos_b; g.act = 1; g.resid = w.sb.x; g.out_f32 = w.sb.x; g.ld_f32 = d; g.rowmap = w.pos_rowmap;
     g.prof_cls = SERENC_PROF_GEMM_POSCONV;
