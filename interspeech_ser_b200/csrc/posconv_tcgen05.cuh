@@ -16,8 +16,9 @@
 //   * accumulators are double-buffered in TMEM (2 x 2 x BN columns); the fused epilogue (bias + exact GELU + fp32
 //     residual add, gap-layout -> packed row map) is the generic one;
 //   * groups narrower than their padding (HuBERT-xlarge: 80 channels in a 128-channel panel pair, 80 outputs in a 128-column
-//     tile) issue only the K = 16 steps that hold real channels (5 of 8 per tap) and N = 80 MMAs: the kernel is bound by the
-//     MMA issue rate at these narrow shapes, so the zero work was 2x of its time.
+//     tile) issue only the K = 16 steps that hold real channels (5 of 8 per tap) and N = 80 MMAs, and the weight box of a
+//     K-block holds 80 rows instead of 128: at these shapes the kernel is bound by MMA issue and by the weight stream out
+//     of L2 (4 MB per 256-row tile with full boxes).
 #pragma once
 #include "gemm_tcgen05.cuh"
 
@@ -122,7 +123,7 @@ posconv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&w_empty[stage], phase ^ 1u);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&w_full[stage], S::W_BYTES);
+            mbar_arrive_expect_tx(&w_full[stage], (uint32_t)cfg.n_mma * 128u);   // the W box holds n_mma rows, not BN
             tma_load_2d(sW + stage * S::W_BYTES, &tmW, &w_full[stage], kb * GEMM_BK, wrow0);
           }
           __syncwarp();

@@ -558,7 +558,7 @@ int launch_posconv_bn(serenc_handle* h, const GemmCall& c, cudaStream_t st) {
   CUtensorMap tA, tW;
   SERENC_TRY(get_tmap(h, c.A, (uint64_t)c.a_cols, (uint64_t)c.a_rows, (uint64_t)c.a_ld * 2, GEMM_BM, &tA));
   const uint64_t wk = c.w_k > 0 ? (uint64_t)c.w_k : (uint64_t)p.num_kb * GEMM_BK;
-  SERENC_TRY(get_tmap(h, c.W, wk, (uint64_t)c.w_rows, wk * 2, BN, &tW));
+  SERENC_TRY(get_tmap(h, c.W, wk, (uint64_t)c.w_rows, wk * 2, (uint32_t)cfg.n_mma, &tW));
   const int64_t tiles = (int64_t)p.tiles_m * p.groups;
   if (tiles <= 0) return 0;
   const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
