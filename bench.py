@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--workloads all|none|a,b,c]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+        (what the driver runs; a bare `python bench.py --gpus N` with N > 1 re-executes itself as that launch)
     python bench.py --impl reference ...     # the reference's own CPU implementation (HF transformers) on host cores
 
 One "step" = one pass of the hot path over one batch of synthetic utterances per GPU:
@@ -701,6 +702,15 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
+        if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+            # `python bench.py --gpus N` typed by hand: become the launch the driver uses (one rank per GPU, rendezvous on 127.0.0.1)
+            import socket
+            with socket.socket() as sk:
+                sk.bind(("127.0.0.1", 0))
+                port = sk.getsockname()[1]
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+            os.execvp(cmd[0], cmd)
         run_ours(args)
 
 

@@ -51,3 +51,38 @@ def test_both_arms_print_the_same_config_and_every_baseline_workload_is_listed()
         assert bench.WORKLOADS[name]["model"] in bench.GOLDEN      # every benched model has a committed HF golden for the in-bench check
     for f in bench.GOLDEN.values():
         assert os.path.isfile(os.path.join(REPO, "tests", "golden", f)), f
+
+
+def test_gpus_n_without_torchrun_relaunches_one_rank_per_gpu(monkeypatch):
+    """`python bench.py --gpus 4` typed by hand execs the driver's torchrun launch (127.0.0.1 rendezvous) with the same flags;
+    under torchrun (WORLD_SIZE set) it does not."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(REPO, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    seen = {}
+
+    class Exec(Exception):
+        pass
+
+    def fake_exec(prog, argv):
+        seen["argv"] = list(argv)
+        raise Exec()
+
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.setattr(bench.os, "execvp", fake_exec)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "4", "--steps", "7", "--warmup", "3"])
+    try:
+        bench.main()
+        assert False, "expected the relaunch"
+    except Exec:
+        pass
+    a = seen["argv"]
+    assert a[1:3] == ["-m", "torch.distributed.run"] and "--nproc-per-node=4" in a and a[a.index("--master-addr") + 1] == "127.0.0.1"
+    assert a[-6:] == ["--gpus", "4", "--steps", "7", "--warmup", "3"] and a[-7].endswith("bench.py")
+    # under torchrun the same flags run in place
+    called = {}
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    monkeypatch.setattr(bench, "run_ours", lambda args: called.setdefault("gpus", args.gpus))
+    bench.main()
+    assert called["gpus"] == 4
